@@ -1,0 +1,156 @@
+/*
+ * macrodna_b200 -- C ABI of the B200-native cell-matching hot path.
+ *
+ * The reference (NakhlehLab/MaCroDNA) is pure Python and has no FFI of its own;
+ * each entry point below replaces a span of src/MaCroDNA/macrodna.py and is what
+ * a ctypes binding on the reference side would bind.
+ * Plain pointers and sizes only; no torch / numpy types.  All matrices are
+ * row-major float64 "cells x genes" (what `df.T.to_numpy()` yields,
+ * macrodna.py:93-94) unless stated otherwise.
+ *
+ * Conventions: every call returns 0 (MCD_OK) or a negative mcd_status;
+ * mcd_last_error(h) gives the detail string of the last failure on a handle.
+ * The caller owns every buffer it passes.  A handle is bound to one CUDA device
+ * and one stream; calls on one handle are serialised by the caller; distinct
+ * handles are independent (no global state).
+ */
+#ifndef MACRODNA_B200_H
+#define MACRODNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCD_ABI_VERSION 1
+
+typedef struct mcd_context* mcd_handle;
+
+typedef enum {
+  MCD_OK = 0,
+  MCD_ERR_INVALID = -1,      /* bad argument (NULL, negative size, ld too small ...)     */
+  MCD_ERR_CUDA = -2,         /* a CUDA runtime call or kernel failed                      */
+  MCD_ERR_NOMEM = -3,        /* device or host allocation failed                          */
+  MCD_ERR_NONFINITE = -4,    /* NaN/Inf in the input data         */
+  MCD_ERR_UNSUPPORTED = -5,  /* precision / shape not supported by this build             */
+  MCD_ERR_NOT_CONVERGED = -6 /* assignment solver hit its iteration guard                 */
+} mcd_status;
+
+/* Arithmetic of the correlation contraction (macrodna.py:103-107). */
+typedef enum {
+  MCD_PREC_FP64 = 0,  /* FP64 tensor-core (DMMA) contraction of centred rows: parity mode   */
+  MCD_PREC_BF16X3 = 1 /* tcgen05 bf16 split-precision (3 slices, 6 products), FP32 in TMEM  */
+} mcd_precision;
+
+/* Where a caller buffer lives. */
+typedef enum { MCD_MEM_HOST = 0, MCD_MEM_DEVICE = 1 } mcd_memspace;
+
+#define MCD_MAX_STEP_STATS 64
+
+/* Per-call measurements, filled when a non-NULL pointer is passed. Times are CUDA-event ms. */
+typedef struct {
+  double ms_h2d;          /* host->device staging of the inputs                          */
+  double ms_standardize;  /* K1 (both operands)                                           */
+  double ms_corr;         /* K2                                                           */
+  double ms_lap;          /* K3+K4, all steps                                             */
+  double ms_d2h;          /* device->host of assign/step/objective                        */
+  double ms_total;        /* first to last event                                          */
+  int64_t n_steps;        /* ceil(M/N), macrodna.py:118-123                               */
+  int64_t kernel_launches; /* kernels launched by this call                               */
+  int64_t lap_rounds;     /* Jacobi bidding rounds, all steps                             */
+  int64_t lap_bids;       /* row scans (one per bidder per round), all steps              */
+  int64_t lap_bytes;      /* cost bytes scanned by bidding + augmentation, all steps      */
+  int64_t lap_aug_rows;   /* persons finished by shortest-augmenting-path instead of bids */
+  int64_t lap_aug_steps;  /* Dijkstra steps of those augmentations                        */
+  double step_ms[MCD_MAX_STEP_STATS];
+  int64_t step_rounds[MCD_MAX_STEP_STATS];
+  int64_t step_bids[MCD_MAX_STEP_STATS];
+} mcd_stats;
+
+int mcd_abi_version(void);
+const char* mcd_strerror(int status);
+
+/* Create / destroy a context on CUDA device `device` (owns a stream + workspace). */
+int mcd_create(mcd_handle* out, int device);
+int mcd_destroy(mcd_handle h);
+const char* mcd_last_error(mcd_handle h);
+int mcd_device_sm_count(mcd_handle h);
+/* Block until everything queued on the handle's stream has finished. */
+int mcd_synchronize(mcd_handle h);
+/* The handle's cudaStream_t (as void*), for callers that record events on it. */
+void* mcd_stream(mcd_handle h);
+
+/*
+ * K1 -- per-cell standardisation.  Replaces the per-operand half of
+ * cosine_similarity_np (macrodna.py:24-25): mean, x - mean, ||x - mean||_2.
+ *   X        [ncells, G] row-major float64, leading dimension ldx (elements), DEVICE
+ *   centred  [ncells, ldk] float64 centred rows, DEVICE; ldk = mcd_padded_k(G);
+ *            columns [G, ldk) are written as zeros (K padding of the contraction)
+ *   norms    [ncells] float64 ||x - mean||, DEVICE
+ * Non-finite input is reported as MCD_ERR_NONFINITE at the next synchronising call
+ * (mcd_check_finite) -- the kernel only raises a device flag.
+ */
+int64_t mcd_padded_k(int64_t G);
+int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
+                    double* centred, double* norms);
+/* Same pass, but emits three bf16 slices of the unit-norm centred row for MCD_PREC_BF16X3:
+ *   slices [3, ncells, ldk16] uint16 (bf16 bits), ldk16 = mcd_padded_k_bf16(G), zero padded. */
+int64_t mcd_padded_k_bf16(int64_t G);
+int mcd_standardize_bf16x3(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
+                           uint16_t* slices, double* norms);
+/* Synchronise and return MCD_ERR_NONFINITE if any standardise call since the last check saw NaN/Inf. */
+int mcd_check_finite(mcd_handle h);
+
+/*
+ * K2 -- correlation matrix.  Replaces the double loop macrodna.py:103-107:
+ *   C[i, j] = dot(a_i, b_j) / (1e-10 + na_i * nb_j)
+ *   A [M, ldk] centred RNA rows, B [N, ldk] centred DNA rows (outputs of mcd_standardize), DEVICE
+ *   C  [M, ldc]  float64 row-major (rows = RNA, columns = DNA, macrodna.py:102), DEVICE, may be NULL
+ *   Ct [N, ldct] float64, the transpose, DEVICE, may be NULL (at least one of C, Ct)
+ */
+int mcd_corr_fp64(mcd_handle h, const double* A, int64_t M, const double* B, int64_t N, int64_t G,
+                  int64_t ldk, const double* nA, const double* nB, double* C, int64_t ldc,
+                  double* Ct, int64_t ldct);
+/* tcgen05 split-precision variant on the bf16 slices of mcd_standardize_bf16x3. */
+int mcd_corr_bf16x3(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
+                    int64_t G, int64_t ldk16, const double* nA, const double* nB, double* C,
+                    int64_t ldc, double* Ct, int64_t ldct);
+
+/*
+ * K3 -- one rectangular assignment.  Replaces one `ilp` call (macrodna.py:27-84):
+ * maximise sum W[i, col4row[i]] over injective maps of the n rows into the m >= n columns.
+ *   W [n, ldw] float64 DEVICE; col4row [n] int32 DEVICE out; objective: DEVICE double out (may be NULL)
+ */
+int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                double* objective);
+
+/*
+ * K3+K4 -- the whole step loop (macrodna.py:110-145) on a resident correlation matrix.
+ *   C [M, ldc], Ct [N, ldct] DEVICE (both required);
+ *   assign [M] int32: DNA column of each RNA row; step [M] int32: 1-based step tag (macrodna.py:139);
+ *   step_obj [ceil(M/N)] float64: per-step objective (`m.objVal`, cf. random_assignment_test.py:91);
+ *   outputs live in `out_space` (host or device).
+ */
+int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, int64_t ldct,
+                  int64_t M, int64_t N, int32_t* assign, int32_t* step, double* step_obj,
+                  int out_space, mcd_stats* stats);
+
+/*
+ * The fused driver: everything between macrodna.py:93 and :145.
+ *   rna [M, G] (ld = ld_rna), dna [N, G] (ld = ld_dna) float64 row-major in `in_space`
+ *   (host buffers are staged through pinned chunks with async copies);
+ *   assign/step/step_obj as above, in `out_space`;
+ *   corr_out: optional [M, N] float64 copy of the correlation matrix in `out_space` (NULL to skip).
+ */
+int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double* dna, int64_t ld_dna,
+                  int64_t M, int64_t N, int64_t G, int in_space, int precision, int32_t* assign,
+                  int32_t* step, double* step_obj, double* corr_out, int out_space, mcd_stats* stats);
+
+/* Number of steps ceil(M/N) (macrodna.py:118-123). */
+int64_t mcd_num_steps(int64_t M, int64_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACRODNA_B200_H */

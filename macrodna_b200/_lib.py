@@ -1,0 +1,195 @@
+"""ctypes binding of ``libmacrodna_b200.so`` (C ABI in ``include/macrodna_b200.h``).
+
+There is no fallback: if the library is missing or no B200 is visible, every
+entry point raises.  Nothing here imports torch or the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmacrodna_b200.so")
+
+MCD_OK = 0
+MCD_ERR_INVALID = -1
+MCD_ERR_CUDA = -2
+MCD_ERR_NOMEM = -3
+MCD_ERR_NONFINITE = -4
+MCD_ERR_UNSUPPORTED = -5
+MCD_ERR_NOT_CONVERGED = -6
+
+PREC = {"fp64": 0, "bf16x3": 1}
+MEM_HOST, MEM_DEVICE = 0, 1
+MAX_STEP_STATS = 64
+
+
+class McdStats(C.Structure):
+    _fields_ = [
+        ("ms_h2d", C.c_double),
+        ("ms_standardize", C.c_double),
+        ("ms_corr", C.c_double),
+        ("ms_lap", C.c_double),
+        ("ms_d2h", C.c_double),
+        ("ms_total", C.c_double),
+        ("n_steps", C.c_int64),
+        ("kernel_launches", C.c_int64),
+        ("lap_rounds", C.c_int64),
+        ("lap_bids", C.c_int64),
+        ("lap_bytes", C.c_int64),
+        ("lap_aug_rows", C.c_int64),
+        ("lap_aug_steps", C.c_int64),
+        ("step_ms", C.c_double * MAX_STEP_STATS),
+        ("step_rounds", C.c_int64 * MAX_STEP_STATS),
+        ("step_bids", C.c_int64 * MAX_STEP_STATS),
+    ]
+
+    def as_dict(self):
+        n = min(int(self.n_steps), MAX_STEP_STATS)
+        d = {k: getattr(self, k) for k, _ in self._fields_[:13]}
+        d["step_ms"] = [self.step_ms[i] for i in range(n)]
+        d["step_rounds"] = [self.step_rounds[i] for i in range(n)]
+        d["step_bids"] = [self.step_bids[i] for i in range(n)]
+        return d
+
+
+# name -> (restype, argtypes); the exact list of symbols include/macrodna_b200.h declares
+_VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SIGNATURES = {
+    "mcd_abi_version": (_I, []),
+    "mcd_strerror": (C.c_char_p, [_I]),
+    "mcd_create": (_I, [C.POINTER(_VP), _I]),
+    "mcd_destroy": (_I, [_VP]),
+    "mcd_last_error": (C.c_char_p, [_VP]),
+    "mcd_device_sm_count": (_I, [_VP]),
+    "mcd_synchronize": (_I, [_VP]),
+    "mcd_stream": (_VP, [_VP]),
+    "mcd_padded_k": (_I64, [_I64]),
+    "mcd_padded_k_bf16": (_I64, [_I64]),
+    "mcd_num_steps": (_I64, [_I64, _I64]),
+    "mcd_standardize": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_standardize_bf16x3": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_check_finite": (_I, [_VP]),
+    "mcd_corr_fp64": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
+    "mcd_corr_bf16x3": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
+    "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
+    "mcd_cell2cell": (
+        _I,
+        [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _I, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)],
+    ),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library and bind every declared symbol.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libmacrodna_b200.so is not built (%s). Run `python -m macrodna_b200.build`; "
+            "there is no CPU fallback." % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mcd_abi_version() != 1:
+        raise RuntimeError("libmacrodna_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class McdError(RuntimeError):
+    def __init__(self, status, detail):
+        super().__init__("macrodna_b200 status %d: %s" % (status, detail))
+        self.status = status
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return int(x)
+
+
+class Handle:
+    """One CUDA device + stream + workspace.  Created lazily so objects holding it stay picklable."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.mcd_create(C.byref(h), int(device))
+        if st != MCD_OK:
+            raise McdError(
+                st,
+                "mcd_create(device=%d) failed: %s -- a B200 (sm_100a) GPU is required, there is no CPU fallback"
+                % (device, self.lib.mcd_strerror(st).decode()),
+            )
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mcd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st):
+        if st != MCD_OK:
+            detail = self.lib.mcd_last_error(self.h).decode()
+            if st == MCD_ERR_NONFINITE or st == MCD_ERR_INVALID:
+                raise ValueError("macrodna_b200: " + detail)
+            raise McdError(st, detail)
+
+    @property
+    def sm_count(self):
+        return self.lib.mcd_device_sm_count(self.h)
+
+    def synchronize(self):
+        self.check(self.lib.mcd_synchronize(self.h))
+
+    # ---- whole path, host or device buffers -------------------------------------------------
+    def cell2cell(self, rna, dna, M, N, G, ld_rna=None, ld_dna=None, in_space=MEM_HOST, precision="fp64",
+                  assign=None, step=None, step_obj=None, corr_out=None, out_space=MEM_HOST):
+        """``rna``/``dna``: numpy arrays (host) or integer device pointers; cells x genes float64."""
+        nsteps = self.lib.mcd_num_steps(M, N)
+        if assign is None:
+            assign = np.empty(M, dtype=np.int32)
+        if step is None:
+            step = np.empty(M, dtype=np.int32)
+        if step_obj is None:
+            step_obj = np.empty(nsteps, dtype=np.float64)
+        stats = McdStats()
+        st = self.lib.mcd_cell2cell(
+            self.h, _ptr(rna), ld_rna or G, _ptr(dna), ld_dna or G, M, N, G, in_space, PREC[precision],
+            _ptr(assign), _ptr(step), _ptr(step_obj), _ptr(corr_out), out_space, C.byref(stats),
+        )
+        self.check(st)
+        return assign, step, step_obj, stats
+
+    def lap_steps(self, C_ptr, ldc, Ct_ptr, ldct, M, N, out_space=MEM_HOST, assign=None, step=None, step_obj=None):
+        nsteps = self.lib.mcd_num_steps(M, N)
+        if assign is None:
+            assign = np.empty(M, dtype=np.int32)
+        if step is None:
+            step = np.empty(M, dtype=np.int32)
+        if step_obj is None:
+            step_obj = np.empty(nsteps, dtype=np.float64)
+        stats = McdStats()
+        st = self.lib.mcd_lap_steps(self.h, _ptr(C_ptr), ldc, _ptr(Ct_ptr), ldct, M, N, _ptr(assign), _ptr(step),
+                                    _ptr(step_obj), out_space, C.byref(stats))
+        self.check(st)
+        return assign, step, step_obj, stats

@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's public class (the drop-in boundary).
+
+``MaCroDNA(rna_df, dna_df, dna_label)`` with ``cell2cell_assignment()`` /
+``cell2clone_assignment()`` / ``tiny_test()`` keeps the constructor, method names,
+return schemas and observable side effects of
+``/root/reference/src/MaCroDNA/macrodna.py:10-17, 86-199, 201-237``.  Pandas gene
+intersection and index bookkeeping stay on the host (north star); everything
+numeric -- standardisation, correlation matrix, the per-step assignment solves and
+the step loop -- runs in the CUDA library behind the C ABI
+(``include/macrodna_b200.h``) through ctypes.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+
+_HANDLES = {}
+
+
+def get_handle(device: int = 0) -> "_lib.Handle":
+    """Per-process, per-device library context (created on first use, so instances pickle)."""
+    h = _HANDLES.get(device)
+    if h is None or h.h is None:
+        h = _lib.Handle(device)
+        _HANDLES[device] = h
+    return h
+
+
+class MaCroDNA:
+    """B200 drop-in for the reference class (``macrodna.py:10``).
+
+    Parameters mirror ``macrodna.py:11``: ``rna_df`` / ``dna_df`` are genes x cells
+    frames (index = gene ids, columns = cell ids, ``:13``); ``dna_label`` has columns
+    ``clone`` and ``cell`` (``:14``).  Keyword-only extras default to reference behaviour:
+
+    * ``precision``: ``"fp64"`` (parity mode, FP64 tensor pipe) or ``"bf16x3"`` (tcgen05 split precision);
+    * ``clone_column``: ``"predict_clone"`` (README.md:201, CRC_data_analysis/macrodna.py:195) or
+      ``"predict"`` (src/MaCroDNA/macrodna.py:198);
+    * ``verbose``: print the reference's progress lines (``:95-98,120,124,147``).
+    """
+
+    def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="fp64",
+                 clone_column="predict_clone", verbose=False):
+        self.rna_df = rna_df
+        self.dna_df = dna_df
+        self.dna_label = dna_label
+        self.device = device
+        self.precision = precision
+        self.clone_column = clone_column
+        self.verbose = verbose
+        self.last_stats = None      # dict of CUDA-event timings / solver counters of the last call
+        self.last_objective = None  # per-step objective (the `m.objVal` of each reference `ilp` call)
+        self.last_assign = None     # int32 DNA column per RNA cell
+        self.last_step = None       # int32 1-based step per RNA cell
+
+    # -- host bookkeeping -------------------------------------------------------------------------
+    def _shared_genes(self):
+        """macrodna.py:89 -- set intersection; canonical order = DNA-frame order."""
+        rna_index = self.rna_df.index
+        dna_index = self.dna_df.index
+        if not dna_index.is_unique or not rna_index.is_unique:
+            raise ValueError("duplicate gene labels in the expression / copy-number index")
+        keep = dna_index.isin(rna_index)
+        genes = dna_index[keep]
+        if len(genes) == 0:
+            raise ValueError("rna_df and dna_df share no genes")
+        return genes
+
+    @staticmethod
+    def _cells_by_genes(df):
+        """macrodna.py:93-94 -- ``df.T.to_numpy()`` as C-contiguous float64 (cells x genes)."""
+        try:
+            a = df.to_numpy(dtype=np.float64).T
+        except (TypeError, ValueError) as e:
+            raise ValueError("non-numeric data in input frame: %s" % e) from None
+        return np.ascontiguousarray(a)
+
+    def _run(self):
+        if self.rna_df is None or self.dna_df is None:
+            raise ValueError("rna_df and dna_df are required")
+        dna_cells = list(self.dna_df.columns)  # macrodna.py:87
+        rna_cells = list(self.rna_df.columns)  # macrodna.py:88
+        if len(set(rna_cells)) != len(rna_cells):
+            # the reference dies later with "1 is not in list" (macrodna.py:159-160)
+            raise ValueError("duplicate RNA cell ids")
+        if len(rna_cells) == 0 or len(dna_cells) == 0:
+            raise ValueError("empty input frame")
+        genes = self._shared_genes()
+        if not (len(genes) == len(self.dna_df.index) and genes.equals(self.dna_df.index)):
+            self.dna_df = self.dna_df.loc[genes, :]  # macrodna.py:90 (observable side effect)
+        if not (len(genes) == len(self.rna_df.index) and genes.equals(self.rna_df.index)):
+            self.rna_df = self.rna_df.loc[genes, :]  # macrodna.py:91
+        dna_np = self._cells_by_genes(self.dna_df)
+        rna_np = self._cells_by_genes(self.rna_df)
+        M, G = rna_np.shape
+        N = dna_np.shape[0]
+        if self.verbose:
+            print("number of cells in dna data %s" % N)
+            print("number of cells in rna data %s" % M)
+            print("number of genes in dna data %s" % G)
+            print("number of genes in rna data %s" % G)
+            q, r = divmod(M, N)
+            print(q, r)
+            print("MaCroDNA will be run for %s steps" % (q + (1 if r else 0)))
+        h = get_handle(self.device)
+        assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, precision=self.precision)
+        if (assign < 0).any():
+            raise ValueError("unassigned RNA cell")  # list.index(1), macrodna.py:160
+        self.last_assign, self.last_step, self.last_objective = assign, step, objs
+        self.last_stats = stats.as_dict()
+        if self.verbose:
+            for o in objs:
+                print("Obj: %g" % o)
+            print("the number of associations in the correspondence matrix %s" % float(M))
+        return rna_cells, dna_cells, assign, step
+
+    # -- public API -------------------------------------------------------------------------------
+    def cell2cell_assignment(self):
+        """macrodna.py:86-186.  Returns ``(df[predict_cell], df[predict_cell, step])``, index ``cell``,
+        rows in RNA input-column order, ``step`` 1-based."""
+        rna_cells, dna_cells, assign, step = self._run()
+        pred = [dna_cells[j] for j in assign.tolist()]
+        tmp_result = pd.DataFrame(list(zip(pred, rna_cells)), columns=["predict_cell", "cell"])
+        tmp_result = tmp_result.set_index("cell")  # macrodna.py:164-165
+        tmp_result_tagged = pd.DataFrame(list(zip(pred, rna_cells, step.tolist())),
+                                         columns=["predict_cell", "cell", "step"])
+        tmp_result_tagged = tmp_result_tagged.set_index("cell")  # macrodna.py:182-184
+        return tmp_result, tmp_result_tagged
+
+    def cell2clone_assignment(self):
+        """macrodna.py:188-199: cell2cell + ``dna_label.set_index("cell").loc[predict_cell]["clone"]``."""
+        if self.dna_label is None:
+            raise ValueError("dna_label is required for cell2clone_assignment")
+        rna_result, _ = self.cell2cell_assignment()
+        dna_label = self.dna_label.set_index("cell")
+        rna_result[self.clone_column] = dna_label.loc[rna_result["predict_cell"]]["clone"].tolist()
+        return rna_result
+
+    def tiny_test(self):
+        """The fixed 4 DNA x 4 RNA x 6-gene case of macrodna.py:201-237 (RNA carries an extra gene g7)."""
+        dna_data = pd.DataFrame.from_dict({"cell1": [2, 2, 3, 1, 6, 2], "cell2": [2, 2, 2, 2, 2, 2],
+                                           "cell3": [1, 1, 2, 2, 2, 3], "cell4": [2, 2, 2, 2, 2, 6],
+                                           "gene": ["g1", "g2", "g3", "g4", "g5", "g6"]}).set_index("gene")
+        rna_data = pd.DataFrame.from_dict({"cell1": [0, 0, 10, 0, 20, 0, 0], "cell2": [2, 2, 2, 2, 2, 2, 0],
+                                           "cell3": [0, 0, 2, 2, 0, 5, 0], "cell4": [1, 1, 1, 1, 1, 20, 0],
+                                           "gene": ["g1", "g2", "g3", "g4", "g5", "g6", "g7"]}).set_index("gene")
+        dna_cluster = pd.DataFrame.from_dict({"clone": [0, 1, 2, 3], "cell": ["cell1", "cell2", "cell3", "cell4"]})
+        print("******Test DNA data is:")
+        print(dna_data)
+        print("******Test RNA data is:")
+        print(rna_data)
+        print("******Clone id for each DNA cell is:")
+        print(dna_cluster)
+        print("**********")
+        print("Start Mapping RNA cells to DNA clones")
+        print("**********")
+        self.dna_df, self.rna_df, self.dna_label = dna_data, rna_data, dna_cluster
+        out = self.cell2clone_assignment()
+        print("**********")
+        print("Finish Mapping")
+        print("Test Success")
+        print("**********")
+        return out

@@ -1,0 +1,586 @@
+// C ABI of the hot path (include/macrodna_b200.h): context, workspace, step loop (K4), fused driver.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mcd_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// context plumbing
+// ------------------------------------------------------------------------------------------------
+int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e) {
+  if (h != nullptr) {
+    char buf[512];
+    if (e != cudaSuccess)
+      snprintf(buf, sizeof buf, "%s: %s (%s)", mcd_strerror(status), what, cudaGetErrorString(e));
+    else
+      snprintf(buf, sizeof buf, "%s: %s", mcd_strerror(status), what);
+    h->err = buf;
+  }
+  return status;
+}
+
+int mcd_ws(mcd_context* h, int slot, size_t bytes, void** out) {
+  mcd_buffer& b = h->ws[slot];
+  if (bytes == 0) bytes = 256;
+  if (b.bytes < bytes) {
+    if (b.ptr != nullptr) {
+      cudaStreamSynchronize(h->stream);
+      cudaFree(b.ptr);
+      b.ptr = nullptr;
+      b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) {
+      b.ptr = nullptr;
+      return mcd_fail(h, MCD_ERR_NOMEM, "cudaMalloc workspace", e);
+    }
+    b.bytes = bytes;
+  }
+  *out = b.ptr;
+  return MCD_OK;
+}
+
+extern "C" {
+
+int mcd_abi_version(void) { return MCD_ABI_VERSION; }
+
+const char* mcd_strerror(int status) {
+  switch (status) {
+    case MCD_OK: return "ok";
+    case MCD_ERR_INVALID: return "invalid argument";
+    case MCD_ERR_CUDA: return "CUDA error";
+    case MCD_ERR_NOMEM: return "out of memory";
+    case MCD_ERR_NONFINITE: return "non-finite value in input";
+    case MCD_ERR_UNSUPPORTED: return "unsupported";
+    case MCD_ERR_NOT_CONVERGED: return "assignment solver did not converge";
+    default: return "unknown status";
+  }
+}
+
+int mcd_create(mcd_handle* out, int device) {
+  if (out == nullptr) return MCD_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MCD_ERR_CUDA;
+  if (device < 0 || device >= ndev) return MCD_ERR_INVALID;
+  mcd_context* h = new (std::nothrow) mcd_context();
+  if (h == nullptr) return MCD_ERR_NOMEM;
+  h->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess && prop.major < 10) {
+    delete h;
+    return MCD_ERR_UNSUPPORTED;  // sm_100a-only build
+  }
+  if (e == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_flags, 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->d_flags, 0, 64, h->stream);
+  if (e != cudaSuccess) {
+    delete h;
+    return MCD_ERR_CUDA;
+  }
+  *out = h;
+  return MCD_OK;
+}
+
+int mcd_destroy(mcd_handle h) {
+  if (h == nullptr) return MCD_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& b : h->ws)
+    if (b.ptr) cudaFree(b.ptr);
+  for (auto ev : h->ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
+  if (h->d_flags) cudaFree(h->d_flags);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return MCD_OK;
+}
+
+const char* mcd_last_error(mcd_handle h) { return h ? h->err.c_str() : "null handle"; }
+int mcd_device_sm_count(mcd_handle h) { return h ? h->sm_count : 0; }
+void* mcd_stream(mcd_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int mcd_synchronize(mcd_handle h) {
+  if (!h) return MCD_ERR_INVALID;
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MCD_OK;
+}
+
+int64_t mcd_padded_k(int64_t G) { return (G + 15) / 16 * 16; }
+int64_t mcd_padded_k_bf16(int64_t G) { return (G + 63) / 64 * 64; }
+int64_t mcd_num_steps(int64_t M, int64_t N) { return N > 0 ? (M + N - 1) / N : 0; }
+
+int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
+                    double* norms) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!X || !centred || !norms || ncells < 0 || G < 1 || ldx < G || G > 0x7fffffff)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_standardize arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  return mcd_launch_standardize(h, X, ncells, G, ldx, centred, mcd_padded_k(G), nullptr, 0, norms);
+}
+
+int mcd_standardize_bf16x3(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, uint16_t* slices,
+                           double* norms) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!X || !slices || !norms || ncells < 0 || G < 1 || ldx < G || G > 0x7fffffff)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_standardize_bf16x3 arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, slices, mcd_padded_k_bf16(G), norms);
+}
+
+int mcd_check_finite(mcd_handle h) {
+  if (!h) return MCD_ERR_INVALID;
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  int flag = 0;
+  MCD_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the expression / copy-number matrix");
+  return MCD_OK;
+}
+
+int mcd_corr_fp64(mcd_handle h, const double* A, int64_t M, const double* B, int64_t N, int64_t G, int64_t ldk,
+                  const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!A || !B || !nA || !nB || (!C && !Ct) || M < 0 || N < 0 || G < 1 || ldk < G || (ldk % 16) != 0 ||
+      (C && ldc < N) || (Ct && ldct < M))
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_fp64 arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  return mcd_launch_corr_fp64(h, A, M, B, N, ldk, nA, nB, C, ldc, Ct, ldct);
+}
+
+int mcd_corr_bf16x3(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N, int64_t G,
+                    int64_t ldk16, const double* nA, const double* nB, double* C, int64_t ldc, double* Ct,
+                    int64_t ldct) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!A3 || !B3 || !nA || !nB || (!C && !Ct) || M < 0 || N < 0 || G < 1 || ldk16 < G || (ldk16 % 64) != 0 ||
+      (C && ldc < N) || (Ct && ldct < M))
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_bf16x3 arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  return mcd_launch_corr_bf16x3(h, A3, M, B3, N, ldk16, nA, nB, C, ldc, Ct, ldct);
+}
+
+int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                double* objective) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!W || !col4row || n < 0 || m < n || ldw < m) return mcd_fail(h, MCD_ERR_INVALID, "mcd_lap_max arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  void* work = nullptr;
+  int st = mcd_ws(h, WS_LAP, mcd_lap_workspace_bytes(n, m) + 256, &work);
+  if (st) return st;
+  // counters live in the first 256 bytes of the slot
+  mcd_lap_counters* cnt = static_cast<mcd_lap_counters*>(work);
+  MCD_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(mcd_lap_counters), h->stream));
+  return mcd_launch_lap(h, W, n, m, ldw, col4row, objective, static_cast<char*>(work) + 256, cnt);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// K4: step-loop bookkeeping kernels (reference macrodna.py:110-145, O(M) instead of dense M x N)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void iota_flags_kernel(int* act, int* flag, int* assign, int* step, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) {
+    act[i] = i;
+    flag[i] = 1;
+    assign[i] = -1;
+    step[i] = 0;
+  }
+}
+
+// W[j, k] = Ct[j, act[k]]  (persons = DNA rows of Ct, objects = still-unassigned RNA cells)
+__global__ void gather_cols_kernel(const double* __restrict__ Ct, int64_t ldct, const int* __restrict__ act, int R,
+                                   double* __restrict__ W, int64_t ldw) {
+  const int64_t j = blockIdx.y;
+  const double* src = Ct + j * ldct;
+  double* dst = W + j * ldw;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) dst[k] = src[act[k]];
+}
+
+// W[k, :] = C[act[k], :]  (persons = still-unassigned RNA cells, objects = DNA cells)
+__global__ void gather_rows_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ act, int N,
+                                   double* __restrict__ W, int64_t ldw) {
+  const int64_t k = blockIdx.y;
+  const double* src = C + (int64_t)act[k] * ldc;
+  double* dst = W + k * ldw;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) dst[j] = src[j];
+}
+
+// persons were DNA cells: col4row[j] = index into act
+__global__ void record_dna_major_kernel(const int* __restrict__ col4row, int N, const int* __restrict__ act,
+                                        int* assign, int* step, int* flag, int tag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) {
+    const int k = col4row[j];
+    if (k >= 0) {
+      const int g = act[k];
+      assign[g] = j;
+      step[g] = tag;
+      flag[g] = 0;
+    }
+  }
+}
+// persons were RNA cells: col4row[k] = DNA column
+__global__ void record_rna_major_kernel(const int* __restrict__ col4row, int R, const int* __restrict__ act,
+                                        int* assign, int* step, int* flag, int tag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < R) {
+    const int j = col4row[k];
+    if (j >= 0) {
+      const int g = act[k];
+      assign[g] = j;
+      step[g] = tag;
+      flag[g] = 0;
+    }
+  }
+}
+
+// Ordered stream compaction of the still-unassigned RNA rows (ascending, macrodna.py:141-145). One CTA.
+__global__ void __launch_bounds__(1024) compact_active_kernel(const int* __restrict__ flag, int M, int* act_out) {
+  __shared__ int sums[1024];
+  const int t = threadIdx.x;
+  const int per = (M + 1023) / 1024;
+  const int lo = min(M, t * per), hi = min(M, lo + per);
+  int c = 0;
+  for (int i = lo; i < hi; ++i) c += flag[i];
+  sums[t] = c;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    const int v = t >= o ? sums[t - o] : 0;
+    __syncthreads();
+    sums[t] += v;
+    __syncthreads();
+  }
+  int pos = sums[t] - c;
+  for (int i = lo; i < hi; ++i)
+    if (flag[i]) act_out[pos++] = i;
+}
+
+cudaEvent_t get_event(mcd_context* h, size_t idx) {
+  while (h->ev.size() <= idx) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev.push_back(e);
+  }
+  return h->ev[idx];
+}
+
+struct StepPlan {
+  int64_t nsteps;
+  size_t w_bytes;
+  size_t lap_bytes;
+};
+
+StepPlan plan_steps(int64_t M, int64_t N) {
+  StepPlan p;
+  p.nsteps = mcd_num_steps(M, N);
+  p.w_bytes = 0;
+  p.lap_bytes = 0;
+  int64_t R = M;
+  for (int64_t s = 0; s < p.nsteps; ++s, R -= N) {
+    const int64_t n = R > N ? N : R;
+    const int64_t m = R > N ? R : N;
+    const size_t lb = mcd_lap_workspace_bytes(n, m);
+    if (lb > p.lap_bytes) p.lap_bytes = lb;
+    if (s > 0) {
+      const size_t wb = (size_t)n * (size_t)((m + 1) & ~1LL) * 8;
+      if (wb > p.w_bytes) p.w_bytes = wb;
+    }
+  }
+  return p;
+}
+
+// Enqueue the whole step loop on h->stream (no host synchronisation: every step's shape is known
+// up front because each non-final step matches exactly N RNA cells).
+// Device outputs: d_assign[M], d_step[M], d_obj[nsteps], d_counters[nsteps].
+int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M,
+                      int64_t N, int* d_assign, int* d_step, double* d_obj, mcd_lap_counters* d_counters,
+                      size_t ev_base) {
+  const StepPlan plan = plan_steps(M, N);
+  void* wbuf = nullptr;
+  void* lapbuf = nullptr;
+  void* stepbuf = nullptr;
+  int st;
+  if ((st = mcd_ws(h, WS_W, plan.w_bytes, &wbuf))) return st;
+  if ((st = mcd_ws(h, WS_LAP, plan.lap_bytes, &lapbuf))) return st;
+  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t ci = ((size_t)(M > N ? M : N) * 4 + 255) / 256 * 256;
+  if ((st = mcd_ws(h, WS_STEP, 3 * mi + ci, &stepbuf))) return st;
+  char* sb = static_cast<char*>(stepbuf);
+  int* act[2] = {reinterpret_cast<int*>(sb), reinterpret_cast<int*>(sb + mi)};
+  int* flag = reinterpret_cast<int*>(sb + 2 * mi);
+  int* col4row = reinterpret_cast<int*>(sb + 3 * mi);
+  double* W = static_cast<double*>(wbuf);
+
+  MCD_CUDA(h, cudaMemsetAsync(d_counters, 0, sizeof(mcd_lap_counters) * plan.nsteps, h->stream));
+  iota_flags_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(act[0], flag, d_assign, d_step, (int)M);
+  MCD_LAUNCH_CHECK(h, "iota_flags_kernel");
+
+  int64_t R = M;
+  int cur = 0;
+  for (int64_t s = 0; s < plan.nsteps; ++s) {
+    if (s < MCD_MAX_STEP_STATS) MCD_CUDA(h, cudaEventRecord(get_event(h, ev_base + s), h->stream));
+    if (R > N) {
+      // all N DNA cells take one RNA cell each (macrodna.py:29,53 with n_min = N)
+      const double* Wp;
+      int64_t ldw;
+      if (s == 0) {
+        Wp = Ct;
+        ldw = ldct;
+      } else {
+        ldw = (R + 1) & ~1LL;
+        dim3 grid((unsigned)((R + 1023) / 1024 < 64 ? (R + 1023) / 1024 : 64), (unsigned)N);
+        gather_cols_kernel<<<grid, 256, 0, h->stream>>>(Ct, ldct, act[cur], (int)R, W, ldw);
+        MCD_LAUNCH_CHECK(h, "gather_cols_kernel");
+        Wp = W;
+      }
+      if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s))) return st;
+      record_dna_major_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(col4row, (int)N, act[cur], d_assign,
+                                                                                 d_step, flag, (int)(s + 1));
+      MCD_LAUNCH_CHECK(h, "record_dna_major_kernel");
+      if (s + 1 < plan.nsteps) {
+        compact_active_kernel<<<1, 1024, 0, h->stream>>>(flag, (int)M, act[cur ^ 1]);
+        MCD_LAUNCH_CHECK(h, "compact_active_kernel");
+        cur ^= 1;
+      }
+    } else {
+      // last step: every remaining RNA cell takes a DNA cell (n_min = |R|)
+      const double* Wp;
+      int64_t ldw;
+      if (s == 0) {
+        Wp = C;
+        ldw = ldc;
+      } else {
+        ldw = (N + 1) & ~1LL;
+        dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), (unsigned)R);
+        gather_rows_kernel<<<grid, 256, 0, h->stream>>>(C, ldc, act[cur], (int)N, W, ldw);
+        MCD_LAUNCH_CHECK(h, "gather_rows_kernel");
+        Wp = W;
+      }
+      if ((st = mcd_launch_lap(h, Wp, R, N, ldw, col4row, d_obj + s, lapbuf, d_counters + s))) return st;
+      record_rna_major_kernel<<<(unsigned)((R + 255) / 256), 256, 0, h->stream>>>(col4row, (int)R, act[cur], d_assign,
+                                                                                 d_step, flag, (int)(s + 1));
+      MCD_LAUNCH_CHECK(h, "record_rna_major_kernel");
+    }
+    R -= N;
+  }
+  MCD_CUDA(h, cudaEventRecord(
+      get_event(h, ev_base + (plan.nsteps < MCD_MAX_STEP_STATS ? plan.nsteps : MCD_MAX_STEP_STATS)), h->stream));
+  return MCD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M, int64_t N,
+                  int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!C || !Ct || !assign || !step || M < 1 || N < 1 || ldc < N || ldct < M || M > 0x3fffffff || N > 0x3fffffff)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_lap_steps arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  const int64_t nsteps = mcd_num_steps(M, N);
+  void* misc = nullptr;
+  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
+  int st = mcd_ws(h, WS_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc);
+  if (st) return st;
+  char* mb = static_cast<char*>(misc);
+  int* d_assign = reinterpret_cast<int*>(mb);
+  int* d_step = reinterpret_cast<int*>(mb + mi);
+  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
+  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
+  const int64_t launches0 = h->launches;
+  const size_t EV_LAP = 8;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP))) return st;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
+
+  const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)M * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)M * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  int bad = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  for (int64_t s = 0; s < nsteps; ++s) {
+    if (hc[s].status) bad = 1;
+    if (stats) {
+      stats->lap_rounds += hc[s].rounds;
+      stats->lap_bids += hc[s].bids;
+      stats->lap_bytes += hc[s].bytes;
+      stats->lap_aug_rows += hc[s].aug_rows;
+      stats->lap_aug_steps += hc[s].aug_steps;
+      if (s < MCD_MAX_STEP_STATS) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));
+        stats->step_ms[s] = ms;
+        stats->step_rounds[s] = hc[s].rounds;
+        stats->step_bids[s] = hc[s].bids;
+      }
+    }
+  }
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
+    stats->ms_lap = ms;
+    stats->ms_total = ms;
+    stats->n_steps = nsteps;
+    stats->kernel_launches = h->launches - launches0;
+  }
+  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  return MCD_OK;
+}
+
+int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double* dna, int64_t ld_dna, int64_t M,
+                  int64_t N, int64_t G, int in_space, int precision, int32_t* assign, int32_t* step, double* step_obj,
+                  double* corr_out, int out_space, mcd_stats* stats) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!rna || !dna || !assign || !step || M < 1 || N < 1 || G < 1 || ld_rna < G || ld_dna < G || M > 0x3fffffff ||
+      N > 0x3fffffff || G > 0x7fffffff)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_cell2cell arguments");
+  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_BF16X3)
+    return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  const int64_t launches0 = h->launches;
+  enum { EV_T0 = 0, EV_H2D, EV_STD, EV_CORR, EV_LAPEND, EV_D2H, EV_LAP = 8 };
+  int st;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_T0), h->stream));
+
+  // ---- stage inputs
+  const double* d_rna = rna;
+  const double* d_dna = dna;
+  int64_t ldr = ld_rna, ldd = ld_dna;
+  if (in_space == MCD_MEM_HOST) {
+    void *pr = nullptr, *pd = nullptr;
+    if ((st = mcd_ws(h, WS_RNA_IN, (size_t)M * G * 8, &pr))) return st;
+    if ((st = mcd_ws(h, WS_DNA_IN, (size_t)N * G * 8, &pd))) return st;
+    MCD_CUDA(h, cudaMemcpy2DAsync(pd, (size_t)G * 8, dna, (size_t)ld_dna * 8, (size_t)G * 8, (size_t)N,
+                                  cudaMemcpyHostToDevice, h->stream));
+    MCD_CUDA(h, cudaMemcpy2DAsync(pr, (size_t)G * 8, rna, (size_t)ld_rna * 8, (size_t)G * 8, (size_t)M,
+                                  cudaMemcpyHostToDevice, h->stream));
+    d_rna = static_cast<const double*>(pr);
+    d_dna = static_cast<const double*>(pd);
+    ldr = ldd = G;
+  }
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_H2D), h->stream));
+
+  // ---- K1 + K2
+  const int64_t ldc = (N + 1) & ~1LL, ldct = (M + 1) & ~1LL;
+  void *pC = nullptr, *pCt = nullptr, *pnA = nullptr, *pnB = nullptr;
+  if ((st = mcd_ws(h, WS_C, (size_t)M * ldc * 8, &pC))) return st;
+  if ((st = mcd_ws(h, WS_CT, (size_t)N * ldct * 8, &pCt))) return st;
+  if ((st = mcd_ws(h, WS_NORM_A, (size_t)M * 8, &pnA))) return st;
+  if ((st = mcd_ws(h, WS_NORM_B, (size_t)N * 8, &pnB))) return st;
+  double* C = static_cast<double*>(pC);
+  double* Ct = static_cast<double*>(pCt);
+  if (precision == MCD_PREC_FP64) {
+    const int64_t ldk = mcd_padded_k(G);
+    void *pa = nullptr, *pb = nullptr;
+    if ((st = mcd_ws(h, WS_RNA_C, (size_t)M * ldk * 8, &pa))) return st;
+    if ((st = mcd_ws(h, WS_DNA_C, (size_t)N * ldk * 8, &pb))) return st;
+    if ((st = mcd_launch_standardize(h, d_rna, M, G, ldr, (double*)pa, ldk, nullptr, 0, (double*)pnA))) return st;
+    if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, (double*)pb, ldk, nullptr, 0, (double*)pnB))) return st;
+    MCD_CUDA(h, cudaEventRecord(get_event(h, EV_STD), h->stream));
+    if ((st = mcd_launch_corr_fp64(h, (double*)pa, M, (double*)pb, N, ldk, (double*)pnA, (double*)pnB, C, ldc, Ct,
+                                   ldct)))
+      return st;
+  } else {
+    const int64_t ldk16 = mcd_padded_k_bf16(G);
+    void *pa = nullptr, *pb = nullptr;
+    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)3 * M * ldk16 * 2, &pa))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)3 * N * ldk16 * 2, &pb))) return st;
+    if ((st = mcd_launch_standardize(h, d_rna, M, G, ldr, nullptr, 0, (uint16_t*)pa, ldk16, (double*)pnA))) return st;
+    if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, (uint16_t*)pb, ldk16, (double*)pnB))) return st;
+    MCD_CUDA(h, cudaEventRecord(get_event(h, EV_STD), h->stream));
+    if ((st = mcd_launch_corr_bf16x3(h, (uint16_t*)pa, M, (uint16_t*)pb, N, ldk16, (double*)pnA, (double*)pnB, C, ldc,
+                                     Ct, ldct)))
+      return st;
+  }
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CORR), h->stream));
+
+  // ---- K3 + K4
+  const int64_t nsteps = mcd_num_steps(M, N);
+  void* misc = nullptr;
+  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
+  if ((st = mcd_ws(h, WS_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc))) return st;
+  char* mb = static_cast<char*>(misc);
+  int* d_assign = reinterpret_cast<int*>(mb);
+  int* d_step = reinterpret_cast<int*>(mb + mi);
+  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
+  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP))) return st;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_LAPEND), h->stream));
+
+  // ---- outputs
+  const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)M * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)M * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  if (corr_out)
+    MCD_CUDA(h, cudaMemcpy2DAsync(corr_out, (size_t)N * 8, C, (size_t)ldc * 8, (size_t)N * 8, (size_t)M, kind,
+                                  h->stream));
+  std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  int flag = 0;
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_D2H), h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+
+  int bad = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  for (int64_t s = 0; s < nsteps; ++s) {
+    if (hc[s].status) bad = 1;
+    if (stats) {
+      stats->lap_rounds += hc[s].rounds;
+      stats->lap_bids += hc[s].bids;
+      stats->lap_bytes += hc[s].bytes;
+      stats->lap_aug_rows += hc[s].aug_rows;
+      stats->lap_aug_steps += hc[s].aug_steps;
+      if (s < MCD_MAX_STEP_STATS) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));
+        stats->step_ms[s] = ms;
+        stats->step_rounds[s] = hc[s].rounds;
+        stats->step_bids[s] = hc[s].bids;
+      }
+    }
+  }
+  if (stats) {
+    auto el = [&](int a, int b) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, get_event(h, a), get_event(h, b));
+      return (double)ms;
+    };
+    stats->ms_h2d = el(EV_T0, EV_H2D);
+    stats->ms_standardize = el(EV_H2D, EV_STD);
+    stats->ms_corr = el(EV_STD, EV_CORR);
+    stats->ms_lap = el(EV_CORR, EV_LAPEND);
+    stats->ms_d2h = el(EV_LAPEND, EV_D2H);
+    stats->ms_total = el(EV_T0, EV_D2H);
+    stats->n_steps = nsteps;
+    stats->kernel_launches = h->launches - launches0;
+  }
+  if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the expression / copy-number matrix");
+  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  return MCD_OK;
+}
+
+}  // extern "C"

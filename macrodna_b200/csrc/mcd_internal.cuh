@@ -1,0 +1,87 @@
+// Internal declarations shared by the kernels and the C ABI (include/macrodna_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/macrodna_b200.h"
+
+struct mcd_buffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct mcd_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  int* d_flags = nullptr;  // [0] non-finite input seen, [1..] spare
+  int64_t launches = 0;
+  // grow-only device workspace slots (reused across calls)
+  mcd_buffer ws[16];
+  // pinned host staging
+  void* h_stage[2] = {nullptr, nullptr};
+  size_t h_stage_bytes = 0;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev;
+};
+
+enum {
+  WS_RNA_IN = 0,   // staged raw RNA rows (host input path)
+  WS_DNA_IN,       // staged raw DNA rows
+  WS_RNA_C,        // centred RNA
+  WS_DNA_C,        // centred DNA
+  WS_NORM_A,
+  WS_NORM_B,
+  WS_C,            // corr [M,N]
+  WS_CT,           // corr^T [N,M]
+  WS_W,            // compacted per-step cost block
+  WS_LAP,          // solver state
+  WS_STEP,         // step-loop state (assign, step, active lists, objectives)
+  WS_SLICES_A,
+  WS_SLICES_B,
+  WS_MISC,
+};
+
+int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);
+int mcd_ws(mcd_context* h, int slot, size_t bytes, void** out);
+
+#define MCD_CUDA(h, call)                                      \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return mcd_fail((h), MCD_ERR_CUDA, #call, e__); \
+  } while (0)
+
+#define MCD_LAUNCH_CHECK(h, name)                              \
+  do {                                                         \
+    (h)->launches++;                                           \
+    cudaError_t e__ = cudaGetLastError();                      \
+    if (e__ != cudaSuccess) return mcd_fail((h), MCD_ERR_CUDA, name, e__); \
+  } while (0)
+
+// ---- kernel launchers (each returns an mcd_status) -------------------------------------------
+int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
+                           double* centred, int64_t ldk, uint16_t* slices, int64_t ldk16, double* norms);
+int mcd_launch_corr_fp64(mcd_context* h, const double* A, int64_t M, const double* B, int64_t N, int64_t ldk,
+                         const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
+int mcd_launch_corr_bf16x3(mcd_context* h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
+                           int64_t ldk16, const double* nA, const double* nB, double* C, int64_t ldc, double* Ct,
+                           int64_t ldct);
+
+struct mcd_lap_counters {  // device-resident, one per solve
+  long long rounds;
+  long long bids;
+  long long bytes;
+  long long aug_rows;
+  long long aug_steps;
+  int status;  // 0 ok, 1 = guard hit
+  int pad;
+};
+size_t mcd_lap_workspace_bytes(int64_t n, int64_t m);
+// Solve one rectangular max-assignment (n <= m).  `work` is mcd_lap_workspace_bytes(n, m) of device memory.
+int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                   double* objective, void* work, mcd_lap_counters* d_counters);

@@ -1,0 +1,226 @@
+// K1 -- per-cell standardisation (HBM-bound streaming kernel).
+//
+// Replaces the per-operand half of cosine_similarity_np (reference
+// src/MaCroDNA/macrodna.py:24-25): for every cell row x[0..G) compute
+//   mean = sum(x)/G,  c = x - mean,  norm = sqrt(sum(c^2))
+// once, instead of twice per (RNA, DNA) pair as the reference does.
+//
+// Layout: X is cells x genes row-major (macrodna.py:93-94 hand-off), so one cell is
+// one contiguous vector.  A group of T threads owns one row and keeps it in
+// registers between the mean pass and the norm pass, so HBM sees exactly one read
+// (8 B/element) and one write (8 B/element FP64 centred rows, or 6 B/element for the
+// three bf16 slices).  Loads/stores are 128-bit and coalesced; reductions are warp
+// shuffles plus one shared-memory hop.
+#include "mcd_internal.cuh"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the T threads that own one row.  `red` has BLOCK/32 doubles.
+template <int T, int BLOCK>
+__device__ __forceinline__ double group_sum(double v, double* red) {
+  v = warp_sum(v);
+  if (T == 32) return v;
+  constexpr int WPG = T / 32;  // warps per row group
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();  // protect `red` reuse between the two reductions
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  const int g0 = (warp / WPG) * WPG;
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < WPG; ++w) s += red[g0 + w];
+  return s;
+}
+
+__device__ __forceinline__ void split_bf16x3(double y, uint16_t& s0, uint16_t& s1, uint16_t& s2) {
+  __nv_bfloat16 b0 = __double2bfloat16(y);
+  double r = y - (double)__bfloat162float(b0);
+  __nv_bfloat16 b1 = __double2bfloat16(r);
+  r -= (double)__bfloat162float(b1);
+  __nv_bfloat16 b2 = __double2bfloat16(r);
+  s0 = __bfloat16_as_ushort(b0);
+  s1 = __bfloat16_as_ushort(b1);
+  s2 = __bfloat16_as_ushort(b2);
+}
+
+// T threads per row, NV double2 per thread (row capacity 2*T*NV elements), VEC = 128-bit loads legal.
+template <int T, int NV, bool VEC>
+__global__ void __launch_bounds__((T > 512 ? T : 512), 1)
+standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ldx, double* __restrict__ Y,
+                 int64_t ldk, uint16_t* __restrict__ S, int64_t ldk16, int64_t slice_stride,
+                 double* __restrict__ norms, int* __restrict__ flags) {
+  constexpr int BLOCK = (T > 512 ? T : 512);
+  constexpr int ROWS = BLOCK / T;
+  __shared__ double red[BLOCK / 32];
+  const int t = threadIdx.x % T;
+  const int64_t row = (int64_t)blockIdx.x * ROWS + threadIdx.x / T;
+  const bool live = row < ncells;
+  const double* x = X + (live ? row : 0) * ldx;
+
+  double2 v[NV];
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int e = 2 * (t + k * T);
+    double2 d = make_double2(0.0, 0.0);
+    if (live) {
+      if (e + 1 < G) {
+        if (VEC) {
+          d = __ldcs(reinterpret_cast<const double2*>(x + e));
+        } else {
+          d.x = __ldcs(x + e);
+          d.y = __ldcs(x + e + 1);
+        }
+      } else if (e < G) {
+        d.x = __ldcs(x + e);
+      }
+    }
+    v[k] = d;
+    sum += d.x + d.y;
+  }
+  sum = group_sum<T, BLOCK>(sum, red);
+  const double mean = sum / (double)G;
+
+  double ss = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int e = 2 * (t + k * T);
+    double cx = (e < G) ? v[k].x - mean : 0.0;
+    double cy = (e + 1 < G) ? v[k].y - mean : 0.0;
+    v[k] = make_double2(cx, cy);
+    ss += cx * cx + cy * cy;
+  }
+  ss = group_sum<T, BLOCK>(ss, red);
+  const double nrm = sqrt(ss);
+  if (!live) return;
+  if (t == 0) {
+    norms[row] = nrm;
+    if (!isfinite(sum) || !isfinite(ss)) atomicOr(flags, 1);
+  }
+
+  if (Y != nullptr) {
+    double* y = Y + row * ldk;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int e = 2 * (t + k * T);
+      if (e + 1 < G) {
+        *reinterpret_cast<double2*>(y + e) = v[k];  // ldk is a multiple of 16 -> aligned
+      } else if (e < G) {
+        y[e] = v[k].x;
+      }
+    }
+    for (int64_t c = G + t; c < ldk; c += T) y[c] = 0.0;
+  }
+  if (S != nullptr) {
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    uint16_t* s0 = S + row * ldk16;
+    uint16_t* s1 = s0 + slice_stride;
+    uint16_t* s2 = s1 + slice_stride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int e = 2 * (t + k * T);
+      if (e < G) {
+        uint16_t a0, a1, a2, b0 = 0, b1 = 0, b2 = 0;
+        split_bf16x3(v[k].x * inv, a0, a1, a2);
+        if (e + 1 < G) split_bf16x3(v[k].y * inv, b0, b1, b2);
+        // e is even and ldk16 is a multiple of 64: 4-byte aligned pair store (pad column is zero)
+        *reinterpret_cast<uint32_t*>(s0 + e) = (uint32_t)a0 | ((uint32_t)b0 << 16);
+        *reinterpret_cast<uint32_t*>(s1 + e) = (uint32_t)a1 | ((uint32_t)b1 << 16);
+        *reinterpret_cast<uint32_t*>(s2 + e) = (uint32_t)a2 | ((uint32_t)b2 << 16);
+      }
+    }
+    const int64_t g2 = (G + 1) & ~1;
+    for (int64_t c = g2 + 2 * t; c < ldk16; c += 2 * T) {
+      *reinterpret_cast<uint32_t*>(s0 + c) = 0u;
+      *reinterpret_cast<uint32_t*>(s1 + c) = 0u;
+      *reinterpret_cast<uint32_t*>(s2 + c) = 0u;
+    }
+  }
+}
+
+// Rows longer than the register-resident capacity: one 512-thread block per row, three sweeps
+// (the row stays L2-resident between sweeps; declared as a 3-read variant in DESIGN.md).
+__global__ void __launch_bounds__(512)
+standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, int64_t ldx, double* __restrict__ Y,
+                      int64_t ldk, uint16_t* __restrict__ S, int64_t ldk16, int64_t slice_stride,
+                      double* __restrict__ norms, int* __restrict__ flags) {
+  __shared__ double red[16];
+  const int64_t row = blockIdx.x;
+  const double* x = X + row * ldx;
+  double sum = 0.0;
+  for (int64_t e = threadIdx.x; e < G; e += 512) sum += x[e];
+  sum = group_sum<512, 512>(sum, red);
+  const double mean = sum / (double)G;
+  double ss = 0.0;
+  for (int64_t e = threadIdx.x; e < G; e += 512) {
+    const double c = x[e] - mean;
+    ss += c * c;
+  }
+  ss = group_sum<512, 512>(ss, red);
+  const double nrm = sqrt(ss);
+  if (threadIdx.x == 0) {
+    norms[row] = nrm;
+    if (!isfinite(sum) || !isfinite(ss)) atomicOr(flags, 1);
+  }
+  const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+  if (Y != nullptr) {
+    double* y = Y + row * ldk;
+    for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = e < G ? x[e] - mean : 0.0;
+  }
+  if (S != nullptr) {
+    uint16_t* s0 = S + row * ldk16;
+    for (int64_t e = threadIdx.x; e < ldk16; e += 512) {
+      uint16_t a0 = 0, a1 = 0, a2 = 0;
+      if (e < G) split_bf16x3((x[e] - mean) * inv, a0, a1, a2);
+      s0[e] = a0;
+      s0[slice_stride + e] = a1;
+      s0[2 * slice_stride + e] = a2;
+    }
+  }
+}
+
+template <int T, int NV>
+int launch_t(mcd_context* h, bool vec, const double* X, int64_t ncells, int G, int64_t ldx, double* Y, int64_t ldk,
+             uint16_t* S, int64_t ldk16, double* norms) {
+  constexpr int BLOCK = (T > 512 ? T : 512);
+  constexpr int ROWS = BLOCK / T;
+  const int64_t grid = (ncells + ROWS - 1) / ROWS;
+  const int64_t stride = ncells * ldk16;
+  if (vec)
+    standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, ldk16, stride,
+                                                                          norms, h->d_flags);
+  else
+    standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, ldk16,
+                                                                           stride, norms, h->d_flags);
+  MCD_LAUNCH_CHECK(h, "standardize_rows");
+  return MCD_OK;
+}
+
+}  // namespace
+
+int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
+                           int64_t ldk, uint16_t* slices, int64_t ldk16, double* norms) {
+  if (ncells == 0) return MCD_OK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
+  const int g = (int)G;
+  if (G <= 256) return launch_t<32, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 1024) return launch_t<128, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 4096) return launch_t<512, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 8192) return launch_t<512, 8>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 12288) return launch_t<512, 12>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 16384) return launch_t<512, 16>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 20480) return launch_t<512, 20>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  if (G <= 24576) return launch_t<512, 24>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
+  standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, ncells, G, ldx, centred, ldk, slices, ldk16,
+                                                                ncells * ldk16, norms, h->d_flags);
+  MCD_LAUNCH_CHECK(h, "standardize_rows_long");
+  return MCD_OK;
+}

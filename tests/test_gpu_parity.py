@@ -1,0 +1,257 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed
+golden fixtures.  Tolerances: correlations <= 1e-6 abs (north star; FP64 path is checked at
+1e-12), per-step objective <= 1e-9 relative, assignments bit-identical except exact ties
+(reported, objective-equal)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_frames, load_reference_cases, tie_report
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_reference_cases()
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def _dev(a):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# the drop-in class against the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_class_matches_reference_run(case):
+    from macrodna_b200 import MaCroDNA
+    from oracle import restatement as R
+
+    rna, dna, lab = case_frames(case)
+    m = MaCroDNA(rna.copy(), dna.copy(), lab.copy(), clone_column=case["clone_column"])
+    res, tagged = m.cell2cell_assignment()
+    assert list(res.index) == case["rna_cells"] and res.index.name == "cell"
+    assert list(res.columns) == ["predict_cell"] and list(tagged.columns) == ["predict_cell", "step"]
+    assert len(m.last_objective) == len(case["printed_obj"])
+    for a, b in zip(m.last_objective, case["printed_obj"]):
+        assert abs(a - b) <= 5e-6 * max(1.0, abs(b))
+    # the side effect of macrodna.py:90-91: frames are gene-filtered in place
+    assert len(m.rna_df.index) == len(m.dna_df.index) == len(set(case["genes_rna"]) & set(case["genes_dna"]))
+    o = R.OracleMaCroDNA(rna.copy(), dna.copy(), lab.copy())
+    o.cell2cell_assignment()
+    assert np.allclose(m.last_objective, o.last["objs"], rtol=1e-12, atol=1e-13)
+    if "dup" in case["name"] or "const" in case["name"]:
+        ident, rep = tie_report(o.last["corrs"], m.last_assign, m.last_step, o.last["assign"], o.last["step"], 1e-12)
+        assert rep["objective_ok"], rep
+        return
+    assert res["predict_cell"].tolist() == case["predict_cell"]
+    assert tagged["step"].tolist() == case["step"]
+    m2 = MaCroDNA(rna.copy(), dna.copy(), lab.copy(), clone_column=case["clone_column"])
+    clone = m2.cell2clone_assignment()
+    assert list(clone.columns) == ["predict_cell", case["clone_column"]]
+    assert clone[case["clone_column"]].tolist() == case["predict_clone"]
+
+
+def test_tiny_test_known_answer(capsys):
+    from macrodna_b200 import MaCroDNA
+
+    m = MaCroDNA(verbose=True)
+    out = m.tiny_test()
+    assert abs(m.last_objective[0] - 2.8300077180864673) < 1e-13  # README.md:138 of the reference
+    assert out["predict_cell"].tolist() == ["cell1", "cell2", "cell3", "cell4"]
+    assert out["predict_clone"].tolist() == [0, 1, 2, 3]
+    txt = capsys.readouterr().out
+    assert "MaCroDNA will be run for 1 steps" in txt and "Obj: 2.83001" in txt and "Test Success" in txt
+
+
+def test_nan_input_raises():
+    from macrodna_b200 import MaCroDNA
+
+    rna, dna, lab = case_frames(CASES[2])
+    rna = rna.astype(float)
+    rna.iloc[3, 2] = np.nan
+    with pytest.raises(ValueError, match="NaN|non-finite"):
+        MaCroDNA(rna, dna).cell2cell_assignment()
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels, one by one, through the C ABI with device pointers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G", [1, 6, 255, 256, 257, 1000, 2000, 4097, 8192, 10000, 15000, 20000, 24576, 30001])
+@pytest.mark.parametrize("odd_ld", [False, True])
+def test_standardize_kernel(handle, G, odd_ld):
+    torch = _torch()
+    from oracle import restatement as R
+
+    rng = np.random.default_rng(G)
+    ncells = 37
+    ld = G + (3 if odd_ld else 0)
+    buf = np.full((ncells, ld), 7.25)
+    x = np.log1p(rng.poisson(4.0, size=(ncells, G)).astype(np.float64)) + rng.random((ncells, G))
+    x[5] = 3.0  # constant cell
+    buf[:, :G] = x
+    d_x = _dev(buf)
+    ldk = handle.lib.mcd_padded_k(G)
+    d_y = torch.full((ncells, ldk), -1.0, dtype=torch.float64, device="cuda")
+    d_n = torch.empty(ncells, dtype=torch.float64, device="cuda")
+    handle.check(handle.lib.mcd_standardize(handle.h, d_x.data_ptr(), ncells, G, ld, d_y.data_ptr(), d_n.data_ptr()))
+    handle.check(handle.lib.mcd_check_finite(handle.h))
+    xc, nrm = R.standardise(x)
+    y = d_y.cpu().numpy()
+    assert np.abs(y[:, :G] - xc).max() <= 1e-13 * max(1.0, np.abs(x).max())
+    assert (y[:, G:] == 0).all()
+    assert np.abs(d_n.cpu().numpy() - nrm).max() <= 1e-12 * max(1.0, nrm.max())
+    assert d_n.cpu().numpy()[5] <= 1e-12 * np.sqrt(G) * 3.0  # zero-variance cell
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 6), (130, 129, 100), (300, 257, 1000), (129, 260, 2001), (1000, 64, 333)])
+def test_corr_fp64_kernel(handle, shape):
+    torch = _torch()
+    from oracle import restatement as R
+
+    M, N, G = shape
+    rng = np.random.default_rng(M * 7 + N)
+    rna = np.log1p(rng.poisson(4.0, size=(M, G)).astype(np.float64))
+    dna = np.log1p(rng.integers(1, 5, size=(N, G)) * (1 + 0.05 * rng.standard_normal((N, G))))
+    if N > 2:
+        dna[1] = 2.0
+    ldk = handle.lib.mcd_padded_k(G)
+    d_a = torch.empty((M, ldk), dtype=torch.float64, device="cuda")
+    d_b = torch.empty((N, ldk), dtype=torch.float64, device="cuda")
+    d_na = torch.empty(M, dtype=torch.float64, device="cuda")
+    d_nb = torch.empty(N, dtype=torch.float64, device="cuda")
+    lib, h = handle.lib, handle.h
+    handle.check(lib.mcd_standardize(h, _dev(rna).data_ptr(), M, G, G, d_a.data_ptr(), d_na.data_ptr()))
+    handle.check(lib.mcd_standardize(h, _dev(dna).data_ptr(), N, G, G, d_b.data_ptr(), d_nb.data_ptr()))
+    ldc, ldct = N + 3, M + 1
+    d_c = torch.full((M, ldc), 9.0, dtype=torch.float64, device="cuda")
+    d_ct = torch.full((N, ldct), 9.0, dtype=torch.float64, device="cuda")
+    handle.check(lib.mcd_corr_fp64(h, d_a.data_ptr(), M, d_b.data_ptr(), N, G, ldk, d_na.data_ptr(), d_nb.data_ptr(),
+                                   d_c.data_ptr(), ldc, d_ct.data_ptr(), ldct))
+    handle.synchronize()
+    c = d_c.cpu().numpy()
+    ct = d_ct.cpu().numpy()
+    ref = R.correlation_matrix(rna, dna)
+    assert np.abs(c[:, :N] - ref).max() < 1e-12
+    assert (c[:, N:] == 9.0).all() and (ct[:, M:] == 9.0).all()  # padding untouched
+    assert (ct[:, :M] == c[:, :N].T).all()  # transpose is bit-identical
+    if N > 2:
+        assert (c[:, 1] == 0).all()  # zero-variance cell gives exactly 0.0 (macrodna.py:25)
+
+
+def _lap_gpu(handle, w):
+    torch = _torch()
+    n, m = w.shape
+    d_w = _dev(w)
+    d_col = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    d_obj = torch.zeros(1, dtype=torch.float64, device="cuda")
+    handle.check(handle.lib.mcd_lap_max(handle.h, d_w.data_ptr(), n, m, m, d_col.data_ptr(), d_obj.data_ptr()))
+    handle.synchronize()
+    return d_col.cpu().numpy(), float(d_obj.cpu().numpy()[0])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (2, 2), (5, 5), (4, 9), (50, 50), (100, 300), (257, 1000),
+                                   (300, 301), (400, 400), (64, 9000), (1000, 1000)])
+def test_lap_random_vs_scipy(handle, shape):
+    from scipy.optimize import linear_sum_assignment
+
+    n, m = shape
+    rng = np.random.default_rng(n * 31 + m)
+    w = rng.standard_normal((n, m)) * 0.1 + 0.05
+    col, obj = _lap_gpu(handle, w)
+    r, c = linear_sum_assignment(w, maximize=True)
+    assert len(np.unique(col)) == n and col.min() >= 0 and col.max() < m
+    ref = w[r, c].sum()
+    assert abs(obj - ref) <= 1e-12 * max(1.0, abs(ref))
+    assert abs(w[np.arange(n), col].sum() - obj) <= 1e-12 * max(1.0, abs(ref))
+    assert (col == c).all()  # generic real costs: the optimum is unique
+
+
+@pytest.mark.parametrize("kind", ["zeros", "small_ints", "dup_cols", "dup_rows", "planted_flat", "negative"])
+def test_lap_ties_and_degenerate(handle, kind):
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(11)
+    n, m = 60, 90
+    if kind == "zeros":
+        w = np.zeros((n, m))
+    elif kind == "small_ints":
+        w = rng.integers(0, 4, size=(n, n)).astype(np.float64)
+    elif kind == "dup_cols":
+        base = rng.random((n, m // 2))
+        w = np.concatenate([base, base], axis=1)
+    elif kind == "dup_rows":
+        base = rng.random((n // 2, m))
+        w = np.concatenate([base, base], axis=0)
+    elif kind == "planted_flat":
+        w = 0.17 + 1e-9 * rng.standard_normal((n, n))
+    else:
+        w = -rng.random((n, n)) - 5.0
+    col, obj = _lap_gpu(handle, w)
+    r, c = linear_sum_assignment(w, maximize=True)
+    assert len(np.unique(col)) == w.shape[0] and col.min() >= 0
+    ref = w[r, c].sum()
+    assert abs(obj - ref) <= 1e-12 * max(1.0, abs(ref)), (obj, ref)
+
+
+@pytest.mark.parametrize("mn", [(9, 4), (3, 7), (5, 5), (8, 4), (5, 1), (1, 1), (1, 3), (101, 10), (64, 64), (130, 64),
+                                (700, 150)])
+def test_step_loop_vs_oracle(handle, mn):
+    torch = _torch()
+    from oracle import restatement as R
+
+    M, N = mn
+    rng = np.random.default_rng(M * 3 + N)
+    corrs = 0.2 * rng.random((M, N)) - 0.03
+    a_ref, s_ref, o_ref = R.step_loop(corrs)
+    d_c = _dev(corrs)
+    d_ct = _dev(corrs.T)
+    a, s, o, stats = handle.lap_steps(d_c.data_ptr(), N, d_ct.data_ptr(), M, M, N)
+    assert (s == s_ref).all() and (a == a_ref).all()
+    assert np.allclose(o, o_ref, rtol=1e-12, atol=1e-14)
+    assert stats.n_steps == R.n_steps(M, N)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path on the seeded synthetic configs against the committed oracle outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
+def test_synthetic_config_vs_golden(handle, name):
+    from macrodna_b200 import synth
+
+    g = np.load(os.path.join(GOLDEN, "synth_%s.npz" % name))
+    inst = synth.make_config_arrays(name)
+    M, G = inst.rna.shape
+    N = inst.dna.shape[0]
+    corr = np.empty((M, N))
+    assign, step, objs, stats = handle.cell2cell(inst.rna, inst.dna, M, N, G, corr_out=corr)
+    # correlations: north-star gate 1e-6 abs; the FP64 path is held to 1e-12
+    assert np.abs(corr[g["sample_i"], g["sample_j"]] - g["sample_corr"]).max() < 1e-12
+    assert abs(corr.sum() - g["corr_sum"][0]) <= 1e-9 * abs(g["corr_sum"][0])
+    assert np.allclose(objs, g["objs"], rtol=1e-9)
+    ident, rep = tie_report(corr, assign, step, g["assign"], g["step"])
+    assert rep["objective_ok"], rep
+    if not ident:
+        # the generator plants one zero-variance DNA cell (an all-zero column: exact ties)
+        print("TIE REPORT", name, rep)
+        assert rep["differing_cells"] <= max(4, M // 200), rep
+    q, r = divmod(M, N)
+    assert np.bincount(step)[1:].tolist() == [N] * q + ([r] if r else [])
+
+
+def test_determinism(handle):
+    from macrodna_b200 import synth
+
+    inst = synth.make_config_arrays("C3", scale=0.25)
+    M, G = inst.rna.shape
+    N = inst.dna.shape[0]
+    a1, s1, o1, _ = handle.cell2cell(inst.rna, inst.dna, M, N, G)
+    a2, s2, o2, _ = handle.cell2cell(inst.rna, inst.dna, M, N, G)
+    assert (a1 == a2).all() and (s1 == s2).all() and (o1 == o2).all()
