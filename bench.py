@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the cell-matching hot path (BASELINE.json metric: ``cell2cell_assignment`` wall-time
+and correlation TFLOP/s).
+
+    python bench.py --gpus N --steps K --warmup W [--workload C5] [--impl reference]
+
+One "step" = one full pass of the hot path (standardise -> correlation matrix -> step loop of
+assignment solves) over one synthetic instance of the workload's shape.  ``value`` is seconds per
+pass with the inputs already resident in HBM; ``e2e`` is the same pass through the C-ABI with
+pinned HOST buffers (H2D of both matrices and D2H of assign/step/objective inside the timed
+region).  Lower is better.  Multi-GPU (N > 1, launched with torch.distributed.run): the RNA rows
+are sharded for standardisation + correlation (no collective in the contraction), the correlation
+shards are all-gathered over NCCL/NVLink, and the assignment step loop runs replicated on every
+rank (identical, deterministic) -- strong scaling of a fixed-size job.
+
+``--impl reference`` times the CPU restatement of the reference's path (oracle/restatement.py: NumPy
+dgemm on all host cores + SciPy linear_sum_assignment) on a bounded sample and extrapolates.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPES = {  # name -> (M, N, G, clones)
+    "C2": (192, 249, 2000, 2),
+    "C3": (2000, 200, 10000, 4),
+    "C4": (5000, 1000, 15000, 8),
+    "C5": (50000, 10000, 20000, 16),
+}
+METRIC = "cell2cell_assignment wall-time"
+UNIT = "s"
+FP64_NOMINAL_TFLOPS = 40.0  # B200 datasheet FP64 (tensor) -- MEASURED_PEAKS.json carries no FP64 figure
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data on the device (same recipe as macrodna_b200/synth.py, torch RNG)
+# ------------------------------------------------------------------------------------------------
+def make_device_instance(torch, M, N, G, clones, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n_seg = -(-G // 50)
+    probs = torch.tensor([0.12, 0.64, 0.16, 0.08], device=device)
+    seg = torch.multinomial(probs.expand(clones, 4), n_seg, replacement=True, generator=g) + 1
+    cn = seg.repeat_interleave(50, dim=1)[:, :G].to(torch.float64)
+    dna_clone = torch.randint(0, clones, (N,), device=device, generator=g)
+    rna_clone = torch.randint(0, clones, (M,), device=device, generator=g)
+    dna = torch.empty((N, G), dtype=torch.float64, device=device)
+    rna = torch.empty((M, G), dtype=torch.float64, device=device)
+    blk = max(1, (1 << 25) // G)
+    for s in range(0, N, blk):
+        e = min(N, s + blk)
+        noise = torch.randn((e - s, G), dtype=torch.float64, device=device, generator=g)
+        dna[s:e] = torch.log1p(torch.clamp(cn[dna_clone[s:e]] * (1.0 + 0.05 * noise), min=0.0))
+    base = torch.exp(torch.randn(G, dtype=torch.float64, device=device, generator=g))
+    lib = torch.exp(0.3 * torch.randn(M, dtype=torch.float64, device=device, generator=g))
+    for s in range(0, M, blk):
+        e = min(M, s + blk)
+        lam = base[None, :] * (cn[rna_clone[s:e]] * 0.5) * lib[s:e, None]
+        counts = torch.poisson(lam.to(torch.float32), generator=g).to(torch.float64) + 1.0
+        rna[s:e] = torch.log1p(counts / counts.sum(dim=1, keepdim=True) * 1e6)
+    return rna, dna, rna_clone, dna_clone
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference's path) on a bounded sample, extrapolated
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(M, N, G, clones, budget_s=20.0):
+    """Times oracle/restatement.py on sub-instances of the workload (same aspect ratio, same gene
+    count) and extrapolates to the full shape: correlation linearly in M*N*G (dgemm-bound),
+    the LSA step loop by a power law in the instance scale fitted on two sub-instances."""
+    from macrodna_b200 import synth
+    from oracle import restatement as R
+
+    cores = os.cpu_count() or 1
+    full_pairs = float(M) * N
+
+    def run(scale):
+        m, n = max(2, int(M * scale)), max(2, int(N * scale))
+        inst = synth.make_arrays(m, n, G, clones, seed=77)
+        t0 = time.perf_counter()
+        corrs = R.correlation_matrix(inst.rna, inst.dna)
+        t1 = time.perf_counter()
+        R.step_loop(corrs)
+        t2 = time.perf_counter()
+        return m, n, t1 - t0, t2 - t1
+
+    if full_pairs * G <= 2.5e11:  # small enough: time the whole workload
+        m, n, tc, tl = run(1.0)
+        return {"value": tc + tl, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "full workload %dx%dx%d: corr %.3fs (dgemm, %d threads) + LSA step loop %.3fs (1 thread)" % (
+                    m, n, G, tc, cores, tl), "corr_s": tc, "lap_s": tl, "extrapolated": False}
+    s1, s2 = 0.05, 0.1
+    m1, n1, tc1, tl1 = run(s1)
+    m2, n2, tc2, tl2 = run(s2)
+    corr_full = tc2 * (full_pairs / (m2 * n2))
+    expo = max(2.0, np.log(max(tl2, 1e-9) / max(tl1, 1e-9)) / np.log(s2 / s1))
+    lap_full = tl2 * (1.0 / s2) ** expo
+    return {"value": corr_full + lap_full, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": True,
+            "corr_s": corr_full, "lap_s": lap_full,
+            "sample": ("sub-instances %dx%d and %dx%d (x%d genes) of the %dx%dx%d workload: corr %.2fs/%.2fs "
+                       "(dgemm on %d threads, extrapolated linearly in M*N*G), LSA step loop %.2fs/%.2fs (1 thread, "
+                       "power law exponent %.2f in scale)") % (m1, n1, m2, n2, G, M, N, G, tc1, tc2, cores, tl1, tl2, expo)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    M, N, G, clones = SHAPES[args.workload]
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base = cpu_baseline(M, N, G, clones)
+        vals.append(base["value"])
+    v = float(np.median(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d RNA x %d DNA x %d genes" % (args.workload, M, N, G)},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MCD_BENCH_WORKLOAD", "C5"), choices=sorted(SHAPES))
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+
+    from macrodna_b200 import _lib, get_handle
+    from macrodna_b200 import dist as mdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    M, N, G, clones = SHAPES[args.workload]
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    peaks = load_peaks()
+    h = get_handle(local_rank)
+    ext = torch.cuda.ExternalStream(h.lib.mcd_stream(h.h), device=device)
+
+    # ---- data: whole instance generated on every rank with the same seed; rank r keeps its RNA shard
+    rna, dna, _, _ = make_device_instance(torch, M, N, G, clones, 1234 + int(args.workload[1:]), device)
+    shard = mdist.row_shard(M, world, rank)
+    rna_loc = rna[shard[0]:shard[1]].contiguous() if world > 1 else rna
+    del rna
+    torch.cuda.synchronize()
+    runner = mdist.ShardedCell2Cell(h, M, N, G, world, rank, device, precision=args.precision)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warm, steps, sample_clocks=False):
+        for _ in range(warm):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record(ext)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, last, clocks
+
+    # ---- value: inputs resident in HBM
+    ms_dev, res_dev, clocks = timed(lambda: runner.run_device(rna_loc, dna), W, K, sample_clocks=True)
+
+    # ---- e2e: pinned host buffers -> C-ABI call -> host results
+    rna_host = torch.empty(rna_loc.shape, dtype=torch.float64, pin_memory=True)
+    dna_host = torch.empty(dna.shape, dtype=torch.float64, pin_memory=True)
+    rna_host.copy_(rna_loc)
+    dna_host.copy_(dna)
+    torch.cuda.synchronize()
+    ms_e2e, res_e2e, _ = timed(lambda: runner.run_host(rna_host, dna_host), 1, K)
+    h2d = rna_host.numel() * 8 + dna_host.numel() * 8
+    d2h = M * 4 * 2 + res_e2e["objs"].size * 8
+
+    if rank == 0:
+        st = res_dev["stats"]
+        nsteps = int(st["n_steps"])
+        # consistency of the two paths and structural invariants at full size
+        assert (res_dev["assign"] == res_e2e["assign"]).all() and (res_dev["step"] == res_e2e["step"]).all()
+        q, r = divmod(M, N)
+        assert np.bincount(res_dev["step"])[1:].tolist() == [N] * q + ([r] if r else [])
+        flops = 2.0 * M * N * G
+        p_mma = 1 if args.precision == "fp64" else 6
+        t_corr = st["ms_corr"] * 1e-3
+        t_std = st["ms_standardize"] * 1e-3
+        t_lap = st["ms_lap"] * 1e-3
+        w_out = 8 if args.precision == "fp64" else 6
+        std_bytes = (M / world + N) * G * (8 + w_out)
+        lap_bytes_alg = sum(max(M - s * N, 0) and (min(M - s * N, N) * max(M - s * N, N) * 8.0) for s in range(nsteps))
+        corr_peak = FP64_NOMINAL_TFLOPS if args.precision == "fp64" else peaks["bf16_tflops"]
+        rooflines = {
+            "standardize": {"bound": "hbm", "achieved": std_bytes / t_std / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": std_bytes / t_std / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                            "peak_source": peaks["source"]},
+            "corr": {"bound": "tensor", "achieved": p_mma * flops / world / t_corr / 1e12, "peak": corr_peak,
+                     "unit": "TFLOP/s", "frac": p_mma * flops / world / t_corr / 1e12 / corr_peak, "traffic": None,
+                     "algorithmic_tflops": flops / world / t_corr / 1e12,
+                     "peak_source": "nominal B200 FP64 (no measured FP64 peak)" if args.precision == "fp64"
+                     else peaks["source"] + " bf16"},
+            "lap": {"bound": "hbm", "achieved": lap_bytes_alg / t_lap / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": lap_bytes_alg / t_lap / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                    "scanned_gbs": st["lap_bytes"] / t_lap / 1e9, "rounds": st["lap_rounds"], "bids": st["lap_bids"],
+                    "aug_rows": st["lap_aug_rows"], "peak_source": peaks["source"]},
+        }
+        dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
+        roof = dict(rooflines[dominant])
+        roof["kernel"] = {"standardize": "standardize_rows", "corr": "corr_fp64_kernel" if args.precision == "fp64"
+                          else "corr_bf16x3_kernel", "lap": "lap_auction_kernel"}[dominant]
+        line = {
+            "metric": METRIC, "value": ms_dev * 1e-3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "fp64" else "bf16x3->f32", "data": "synthetic",
+            "config": {"workload": "%s: %d RNA x %d DNA x %d genes, %d steps" % (args.workload, M, N, G, nsteps),
+                       "precision": args.precision, "l2": "inputs (%.1f GB) larger than L2" % ((M + N) * G * 8 / 1e9),
+                       "parallelism": "rna-row-sharded corr x%d + allgather + replicated LAP" % world if world > 1
+                       else "single GPU"},
+            "corr_tflops": flops / world / t_corr / 1e12,
+            "stage_ms": {k: st[k] for k in ("ms_h2d", "ms_standardize", "ms_corr", "ms_lap", "ms_d2h", "ms_total")},
+            "lap_step_ms": st["step_ms"], "lap_step_rounds": st["step_rounds"],
+            "e2e": {"value": ms_e2e * 1e-3, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "stage_ms": {k: res_e2e["stats"][k] for k in ("ms_h2d", "ms_standardize", "ms_corr", "ms_lap",
+                                                                   "ms_d2h", "ms_total")}},
+            "gpu_launches": int(st["kernel_launches"]) * K,
+            "clocks": clocks,
+            "roofline": roof,
+            "rooflines": rooflines,
+            "objective": [float(x) for x in res_dev["objs"]],
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(M, N, G, clones)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,14 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
                   int64_t M, int64_t N, int64_t G, int in_space, int precision, int32_t* assign,
                   int32_t* step, double* step_obj, double* corr_out, int out_space, mcd_stats* stats);
 
+/*
+ * Out-of-place transpose of a row-major float64 matrix: dst[c, r] = src[r, c], src [rows, lds],
+ * dst [cols, ldd], both DEVICE.  Used by the multi-GPU driver to rebuild C^T after the NCCL
+ * all-gather of the row-sharded correlation matrix.
+ */
+int mcd_transpose_f64(mcd_handle h, const double* src, int64_t rows, int64_t cols, int64_t lds, double* dst,
+                      int64_t ldd);
+
 /* Number of steps ceil(M/N) (macrodna.py:118-123). */
 int64_t mcd_num_steps(int64_t M, int64_t N);
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "mcd_check_finite": (_I, [_VP]),
     "mcd_corr_fp64": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_corr_bf16x3": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
+    "mcd_transpose_f64": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I64]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
     "mcd_cell2cell": (

@@ -269,6 +269,22 @@ __global__ void __launch_bounds__(1024) compact_active_kernel(const int* __restr
     if (flag[i]) act_out[pos++] = i;
 }
 
+// dst[c, r] = src[r, c] through a padded 32x32 shared tile (coalesced on both sides)
+__global__ void transpose_f64_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t lds,
+                                     double* __restrict__ dst, int64_t ldd) {
+  __shared__ double tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * lds + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
 cudaEvent_t get_event(mcd_context* h, size_t idx) {
   while (h->ev.size() <= idx) {
     cudaEvent_t e;
@@ -385,6 +401,30 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
 }  // namespace
 
 extern "C" {
+
+int mcd_transpose_f64(mcd_handle h, const double* src, int64_t rows, int64_t cols, int64_t lds, double* dst,
+                      int64_t ldd) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!src || !dst || rows < 0 || cols < 0 || lds < cols || ldd < rows)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_transpose_f64 arguments");
+  if (rows == 0 || cols == 0) return MCD_OK;
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  const int64_t gy = (rows + 31) / 32;
+  if (gy > 65535) {
+    // split the row range so gridDim.y stays legal
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535LL * 32) {
+      const int64_t nr = rows - r0 < 65535LL * 32 ? rows - r0 : 65535LL * 32;
+      dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((nr + 31) / 32));
+      transpose_f64_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(src + r0 * lds, nr, cols, lds, dst + r0, ldd);
+      MCD_LAUNCH_CHECK(h, "transpose_f64_kernel");
+    }
+    return MCD_OK;
+  }
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)gy);
+  transpose_f64_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(src, rows, cols, lds, dst, ldd);
+  MCD_LAUNCH_CHECK(h, "transpose_f64_kernel");
+  return MCD_OK;
+}
 
 int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M, int64_t N,
                   int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats) {

@@ -35,7 +35,10 @@ class Instance:
     dna_clone: np.ndarray  # [N]
 
 
-def make_arrays(n_rna, n_dna, n_genes, n_clones, seed, constant_dna_cell=True, dtype=np.float64) -> Instance:
+def make_arrays(n_rna, n_dna, n_genes, n_clones, seed, constant_dna_cell=False, dtype=np.float64) -> Instance:
+    """``constant_dna_cell=True`` plants one zero-variance DNA cell (an all-copy-number-2 profile, as the
+    reference's CRC data contains): its correlations are exactly 0.0, i.e. an exact tie by construction --
+    which RNA cell it takes in a step is arbitrary and cascades into the later steps' sub-problems."""
     rng = np.random.default_rng(seed)
     # piecewise-constant copy-number profiles over ~50-gene segments, mostly 2
     n_seg = max(1, -(-n_genes // 50))
@@ -63,13 +66,13 @@ def make_arrays(n_rna, n_dna, n_genes, n_clones, seed, constant_dna_cell=True, d
     return Instance(rna=rna, dna=dna, rna_clone=rna_clone, dna_clone=dna_clone)
 
 
-def make_config_arrays(name: str, seed: int | None = None, scale: float = 1.0) -> Instance:
+def make_config_arrays(name: str, seed: int | None = None, scale: float = 1.0, ties: bool = False) -> Instance:
     m, n, g, k = CONFIG_SHAPES[name]
     if scale != 1.0:
         m, n, g = max(2, int(m * scale)), max(2, int(n * scale)), max(8, int(g * scale))
     if seed is None:
         seed = 1234 + int(name[1:])
-    return make_arrays(m, n, g, k, seed)
+    return make_arrays(m, n, g, k, seed, constant_dna_cell=ties)
 
 
 def make_frames(inst: Instance, extra_rna_genes: float = 0.03, seed: int = 0, rna_ids=None, dna_ids=None):
