@@ -55,9 +55,8 @@ struct LapState {
   const double* W;
   int n, m;
   int64_t ldw;
-  int chunk;    // objects per scan chunk
-  int nchunks;  // ceil(m / chunk)
-  int vec;      // 128-bit loads legal
+  int max_chunks;  // upper bound on chunks per row (partial-result slots = grid size)
+  int vec;         // 128-bit loads legal
   double* price;     // [m]
   int* owner;        // [m]
   unsigned long long* key;  // [m]
@@ -67,10 +66,10 @@ struct LapState {
   double* gam;       // [n] bid increment per list slot
   int* un[2];        // [n] bidder lists
   int* done;         // [n] chunks finished per list slot
-  double* pv1;       // [n * nchunks] partial best
-  double* pv2;       // [n * nchunks] partial second
-  int* pj1;          // [n * nchunks]
-  int* pj2;          // [n * nchunks]
+  double* pv1;       // [grid slots] partial best
+  double* pv2;       // [grid slots] partial second
+  int* pj1;          // [grid slots]
+  int* pj2;          // [grid slots]
   // augmentation scratch
   double* sp;        // [m] shortest path cost
   int* pred;         // [m]
@@ -99,6 +98,18 @@ __device__ __forceinline__ void top2_push(Top2& t, double v, int j) {
     t.v1 = v;
     t.j1 = j;
   } else if (better(v, j, t.v2, t.j2)) {
+    t.v2 = v;
+    t.j2 = j;
+  }
+}
+// in-thread variant: candidates arrive in increasing j, so strict '>' keeps the smallest index on ties
+__device__ __forceinline__ void top2_push_seq(Top2& t, double v, int j) {
+  if (v > t.v1) {
+    t.v2 = t.v1;
+    t.j2 = t.j1;
+    t.v1 = v;
+    t.j1 = j;
+  } else if (v > t.v2) {
     t.v2 = v;
     t.j2 = j;
   }
@@ -181,28 +192,53 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
       }
       // ---- bidding: (list slot, chunk) work items over the whole grid
       const int* un = s.un[cur];
-      const long long items = (long long)nu * s.nchunks;
+      // few bidders: split every row over ~grid/nu CTAs so the round costs one memory latency, not a row sweep
+      int nch = 1;
+      if (nu < (int)gridDim.x) nch = min(s.max_chunks, (int)gridDim.x / nu);
+      const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
+      const long long items = (long long)nu * nch;
       for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const int k = (int)(item / s.nchunks);
-        const int c = (int)(item - (long long)k * s.nchunks);
+        const int k = (int)(item / nch);
+        const int c = (int)(item - (long long)k * nch);
         const int i = un[k];
         const double* w = s.W + (int64_t)i * s.ldw;
-        const int j0 = c * s.chunk;
-        const int j1 = min(s.m, j0 + s.chunk);
+        const int j0 = min(s.m, c * chunk);
+        const int j1 = min(s.m, j0 + chunk);
         Top2 t{NEG_INF, NEG_INF, -1, -1};
         if (s.vec) {
-          for (int j = j0 + 2 * tid; j < j1; j += 2 * LAP_THREADS) {
+          constexpr int S = 2 * LAP_THREADS;
+          int j = j0 + 2 * tid;
+          // 4 independent 128-bit load pairs in flight per thread (latency-bound when few rows are active)
+          for (; j + 3 * S + 1 < j1; j += 4 * S) {
+            const double2 w0 = __ldg(reinterpret_cast<const double2*>(w + j));
+            const double2 w1 = __ldg(reinterpret_cast<const double2*>(w + j + S));
+            const double2 w2 = __ldg(reinterpret_cast<const double2*>(w + j + 2 * S));
+            const double2 w3 = __ldg(reinterpret_cast<const double2*>(w + j + 3 * S));
+            const double2 p0 = *reinterpret_cast<const double2*>(s.price + j);
+            const double2 p1 = *reinterpret_cast<const double2*>(s.price + j + S);
+            const double2 p2 = *reinterpret_cast<const double2*>(s.price + j + 2 * S);
+            const double2 p3 = *reinterpret_cast<const double2*>(s.price + j + 3 * S);
+            top2_push_seq(t, w0.x - p0.x, j);
+            top2_push_seq(t, w0.y - p0.y, j + 1);
+            top2_push_seq(t, w1.x - p1.x, j + S);
+            top2_push_seq(t, w1.y - p1.y, j + S + 1);
+            top2_push_seq(t, w2.x - p2.x, j + 2 * S);
+            top2_push_seq(t, w2.y - p2.y, j + 2 * S + 1);
+            top2_push_seq(t, w3.x - p3.x, j + 3 * S);
+            top2_push_seq(t, w3.y - p3.y, j + 3 * S + 1);
+          }
+          for (; j < j1; j += S) {
             if (j + 1 < j1) {
-              const double2 wv = *reinterpret_cast<const double2*>(w + j);
+              const double2 wv = __ldg(reinterpret_cast<const double2*>(w + j));
               const double2 pv = *reinterpret_cast<const double2*>(s.price + j);
-              top2_push(t, wv.x - pv.x, j);
-              top2_push(t, wv.y - pv.y, j + 1);
+              top2_push_seq(t, wv.x - pv.x, j);
+              top2_push_seq(t, wv.y - pv.y, j + 1);
             } else {
-              top2_push(t, w[j] - s.price[j], j);
+              top2_push_seq(t, __ldg(w + j) - s.price[j], j);
             }
           }
         } else {
-          for (int j = j0 + tid; j < j1; j += LAP_THREADS) top2_push(t, w[j] - s.price[j], j);
+          for (int j = j0 + tid; j < j1; j += LAP_THREADS) top2_push_seq(t, __ldg(w + j) - s.price[j], j);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -214,21 +250,21 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
         if (tid == 0) {
 #pragma unroll
           for (int wi = 1; wi < LAP_THREADS / 32; ++wi) top2_merge(t, wred[wi]);
-          if (s.nchunks == 1) {
+          if (nch == 1) {
             finalize_bid(s, k, i, t, eps);
           } else {
-            const int64_t slot = (int64_t)k * s.nchunks + c;
+            const int64_t slot = (int64_t)k * nch + c;
             s.pv1[slot] = t.v1;
             s.pv2[slot] = t.v2;
             s.pj1[slot] = t.j1;
             s.pj2[slot] = t.j2;
             __threadfence();
             const int prev = atomicAdd(&s.done[k], 1);
-            if (prev == s.nchunks - 1) {
+            if (prev == nch - 1) {
               __threadfence();
               Top2 a{NEG_INF, NEG_INF, -1, -1};
-              for (int cc = 0; cc < s.nchunks; ++cc) {
-                const int64_t sl = (int64_t)k * s.nchunks + cc;
+              for (int cc = 0; cc < nch; ++cc) {
+                const int64_t sl = (int64_t)k * nch + cc;
                 Top2 b{__ldcg(&s.pv1[sl]), __ldcg(&s.pv2[sl]), __ldcg(&s.pj1[sl]), __ldcg(&s.pj2[sl])};
                 top2_merge(a, b);
               }
@@ -517,20 +553,23 @@ __global__ void __launch_bounds__(1024) lap_objective_kernel(const double* __res
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int pick_chunk(int64_t m) {
-  const char* e = getenv("MCD_LAP_CHUNK");
-  int chunk = e ? atoi(e) : 8192;
-  if (chunk < 512) chunk = 512;
-  chunk &= ~1;
-  (void)m;
-  return chunk;
+constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size (sm_count * blocks/SM)
+
+int pick_max_chunks(int64_t m) {
+  const char* e = getenv("MCD_LAP_MIN_CHUNK");
+  int min_chunk = e ? atoi(e) : 1024;  // objects per CTA below which splitting stops paying
+  if (min_chunk < 2) min_chunk = 2;
+  int64_t mc = m / min_chunk;
+  if (mc < 1) mc = 1;
+  if (mc > 256) mc = 256;
+  return (int)mc;
 }
 
 }  // namespace
 
 size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
-  const int chunk = pick_chunk(m);
-  const int64_t nch = (m + chunk - 1) / chunk;
+  const int64_t nch = 1;
+  (void)nch;
   size_t b = 0;
   b += align_up(sizeof(LapCtrl), 256);
   b += align_up(m * 8, 256);          // price
@@ -541,8 +580,8 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up(n * 8, 256);          // gam
   b += 2 * align_up(n * 4, 256);      // un lists
   b += align_up(n * 4, 256);          // done
-  b += 2 * align_up(n * nch * 8, 256);  // pv1 pv2
-  b += 2 * align_up(n * nch * 4, 256);  // pj1 pj2
+  b += 2 * align_up(MAX_GRID_SLOTS * 8, 256);  // pv1 pv2
+  b += 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // pj1 pj2
   b += align_up(m * 8, 256);          // sp
   b += align_up(m * 4, 256);          // pred
   b += align_up((n + 1) * 4, 256);    // sc_col
@@ -560,8 +599,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.n = (int)n;
   s.m = (int)m;
   s.ldw = ldw;
-  s.chunk = pick_chunk(m);
-  s.nchunks = (int)((m + s.chunk - 1) / s.chunk);
+  s.max_chunks = pick_max_chunks(m);
   s.vec = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldw & 1) == 0);
   char* p = static_cast<char*>(work);
   auto take = [&](size_t bytes) {
@@ -579,10 +617,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.un[0] = reinterpret_cast<int*>(take(n * 4));
   s.un[1] = reinterpret_cast<int*>(take(n * 4));
   s.done = reinterpret_cast<int*>(take(n * 4));
-  s.pv1 = reinterpret_cast<double*>(take(n * s.nchunks * 8));
-  s.pv2 = reinterpret_cast<double*>(take(n * s.nchunks * 8));
-  s.pj1 = reinterpret_cast<int*>(take(n * s.nchunks * 4));
-  s.pj2 = reinterpret_cast<int*>(take(n * s.nchunks * 4));
+  s.pv1 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
+  s.pv2 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
+  s.pj1 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
+  s.pj2 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
   s.sp = reinterpret_cast<double*>(take(m * 8));
   s.pred = reinterpret_cast<int*>(take(m * 4));
   s.sc_col = reinterpret_cast<int*>(take((n + 1) * 4));
@@ -609,7 +647,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (per_sm < 1) return mcd_fail(h, MCD_ERR_CUDA, "lap_auction_kernel cannot be resident");
   int want = (e = getenv("MCD_LAP_BLOCKS_PER_SM")) ? atoi(e) : 4;
   if (want < 1) want = 1;
-  const int blocks = h->sm_count * (per_sm < want ? per_sm : want);
+  int blocks = h->sm_count * (per_sm < want ? per_sm : want);
+  if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
   void* args[] = {&s};
   MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                           h->stream));

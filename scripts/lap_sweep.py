@@ -1,0 +1,28 @@
+"""Sweep solver knobs (env vars read per solve) on a synthetic workload; prints per-step ms / rounds."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from macrodna_b200 import get_handle, _lib
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "C5"
+M, N, G, clones = bench.SHAPES[wl]
+dev = torch.device("cuda", 0)
+rna, dna, _, _ = bench.make_device_instance(torch, M, N, G, clones, 1234 + int(wl[1:]), dev)
+h = get_handle(0)
+settings = [dict(x.split("=") for x in s.split(",") if x) for s in sys.argv[2:]] or [{}]
+ref = None
+for st in settings:
+    for k, v in st.items():
+        os.environ[k] = v
+    for rep in range(2):
+        a, s_, o, stats = h.cell2cell(rna.data_ptr(), dna.data_ptr(), M, N, G, in_space=_lib.MEM_DEVICE)
+    d = stats.as_dict()
+    if ref is None:
+        ref = (a.copy(), o.copy())
+    same = bool((a == ref[0]).all())
+    print(json.dumps({"set": st, "ms_lap": round(d["ms_lap"], 2), "step_ms": [round(x, 2) for x in d["step_ms"]],
+                      "rounds": d["step_rounds"], "bids": d["lap_bids"], "aug": [d["lap_aug_rows"], d["lap_aug_steps"]],
+                      "same_as_first": same, "ms_corr": round(d["ms_corr"], 2)}), flush=True)
+    for k in st:
+        del os.environ[k]
