@@ -28,15 +28,42 @@
 //
 // Bound: HBM/L2 bandwidth in the wide rounds (each bid reads one cost row: 8 B/object),
 // launch/sync latency in the narrow ones.
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 
 #include "mcd_internal.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace {
+
+// Grid-wide barrier for the persistent auction kernel (launched with cudaLaunchCooperativeKernel so
+// all CTAs are co-resident).  One monotonic counter; each CTA's thread 0 arrives with a RELEASE
+// reduction (MEMBAR.ALL.GPU + REDG) and spins on a relaxed gpu-scope load.  There is deliberately
+// no acquire fence: on sm_100a every gpu-scope acquire (ld.acquire, fence.acq_rel, __threadfence,
+// cooperative_groups grid.sync) ends in CCTL.IVALL, a whole-L1 invalidate that ncu shows costing
+// ~4x the actual wait in this latency-bound round loop.  Instead every load of state that other
+// CTAs mutate goes through ldm() = ld.global.cg (L2, the coherence point), so there is no stale L1
+// line to drop.  The cost matrix W is immutable during the kernel and keeps the cached path.
+struct GridBarrier {
+  unsigned int* counter;
+  unsigned int target;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += gridDim.x;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+      unsigned int seen;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      } while ((int)(seen - target) < 0);
+    }
+    __syncthreads();
+  }
+};
+
+// load of inter-CTA mutable state: L2-coherent, never served from a stale L1 line
+template <typename T>
+__device__ __forceinline__ T ldm(const T* p) {
+  return __ldcg(p);
+}
 
 constexpr int LAP_THREADS = 256;
 constexpr int JV_THREADS = 1024;
@@ -48,7 +75,8 @@ struct LapCtrl {
   int cur;          // which list is current
   int stalled;      // phase A ended with bidders left
   double wmin, wmax;
-  int pad[2];
+  unsigned int barrier;  // GridBarrier counter
+  int pad[1];
 };
 
 struct LapState {
@@ -64,6 +92,7 @@ struct LapState {
   int* col4row;      // [n]  (caller's output)
   int* bj;           // [n] bid object per list slot
   double* gam;       // [n] bid increment per list slot
+  double* bval;      // [n] bidder's value (W - price) of the object it bids on, per list slot
   int* un[2];        // [n] bidder lists
   int* done;         // [n] chunks finished per list slot
   double* pv1;       // [grid slots] partial best
@@ -136,16 +165,17 @@ __device__ __forceinline__ unsigned long long pack_bid(double gamma, int person)
 // Record the bid of list slot k (person i) once its whole row has been scanned.
 __device__ __forceinline__ void finalize_bid(const LapState& s, int k, int i, Top2 t, double eps) {
   int j = t.j1;
-  if (eps == 0.0 && t.j2 >= 0 && t.v1 == t.v2 && s.owner[j] >= 0 && s.owner[t.j2] < 0) j = t.j2;  // exact tie
+  if (eps == 0.0 && t.j2 >= 0 && t.v1 == t.v2 && ldm(&s.owner[j]) >= 0 && ldm(&s.owner[t.j2]) < 0) j = t.j2;  // exact tie
   const double gamma = (t.j2 >= 0 ? (t.v1 - t.v2) : 0.0) + eps;
   s.bj[k] = j;
   s.gam[k] = gamma;
+  s.bval[k] = (j == t.j1) ? t.v1 : t.v2;
   atomicMax(&s.key[j], pack_bid(gamma, i));
 }
 
 // Phase A.  One cooperative launch runs every round of every eps phase.
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
-  cg::grid_group grid = cg::this_grid();
+  GridBarrier grid{&s.ctrl->barrier, 0u};
   __shared__ Top2 wred[LAP_THREADS / 32];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -160,6 +190,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
   const bool scaling = s.square_scaling && range > 0.0;
   if (scaling) eps = range / s.theta;
   long long rounds = 0, bids = 0, bytes = 0;
+  long long tph[4] = {0, 0, 0, 0};
   bool guard_hit = false;
 
   for (;;) {  // eps phases
@@ -191,6 +222,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
         break;
       }
       // ---- bidding: (list slot, chunk) work items over the whole grid
+      const long long t0 = clock64();
       const int* un = s.un[cur];
       // few bidders: split every row over ~grid/nu CTAs so the round costs one memory latency, not a row sweep
       int nch = 1;
@@ -200,7 +232,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
       for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const int k = (int)(item / nch);
         const int c = (int)(item - (long long)k * nch);
-        const int i = un[k];
+        const int i = ldm(&un[k]);
         const double* w = s.W + (int64_t)i * s.ldw;
         const int j0 = min(s.m, c * chunk);
         const int j1 = min(s.m, j0 + chunk);
@@ -214,10 +246,10 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
             const double2 w1 = __ldg(reinterpret_cast<const double2*>(w + j + S));
             const double2 w2 = __ldg(reinterpret_cast<const double2*>(w + j + 2 * S));
             const double2 w3 = __ldg(reinterpret_cast<const double2*>(w + j + 3 * S));
-            const double2 p0 = *reinterpret_cast<const double2*>(s.price + j);
-            const double2 p1 = *reinterpret_cast<const double2*>(s.price + j + S);
-            const double2 p2 = *reinterpret_cast<const double2*>(s.price + j + 2 * S);
-            const double2 p3 = *reinterpret_cast<const double2*>(s.price + j + 3 * S);
+            const double2 p0 = ldm(reinterpret_cast<const double2*>(s.price + j));
+            const double2 p1 = ldm(reinterpret_cast<const double2*>(s.price + j + S));
+            const double2 p2 = ldm(reinterpret_cast<const double2*>(s.price + j + 2 * S));
+            const double2 p3 = ldm(reinterpret_cast<const double2*>(s.price + j + 3 * S));
             top2_push_seq(t, w0.x - p0.x, j);
             top2_push_seq(t, w0.y - p0.y, j + 1);
             top2_push_seq(t, w1.x - p1.x, j + S);
@@ -230,15 +262,15 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
           for (; j < j1; j += S) {
             if (j + 1 < j1) {
               const double2 wv = __ldg(reinterpret_cast<const double2*>(w + j));
-              const double2 pv = *reinterpret_cast<const double2*>(s.price + j);
+              const double2 pv = ldm(reinterpret_cast<const double2*>(s.price + j));
               top2_push_seq(t, wv.x - pv.x, j);
               top2_push_seq(t, wv.y - pv.y, j + 1);
             } else {
-              top2_push_seq(t, __ldg(w + j) - s.price[j], j);
+              top2_push_seq(t, __ldg(w + j) - ldm(&s.price[j]), j);
             }
           }
         } else {
-          for (int j = j0 + tid; j < j1; j += LAP_THREADS) top2_push_seq(t, __ldg(w + j) - s.price[j], j);
+          for (int j = j0 + tid; j < j1; j += LAP_THREADS) top2_push_seq(t, __ldg(w + j) - ldm(&s.price[j]), j);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -258,10 +290,9 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
             s.pv2[slot] = t.v2;
             s.pj1[slot] = t.j1;
             s.pj2[slot] = t.j2;
-            __threadfence();
-            const int prev = atomicAdd(&s.done[k], 1);
+            int prev;  // release: the partial above is visible before the count; no L1-invalidating fence
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[k]) : "memory");
             if (prev == nch - 1) {
-              __threadfence();
               Top2 a{NEG_INF, NEG_INF, -1, -1};
               for (int cc = 0; cc < nch; ++cc) {
                 const int64_t sl = (int64_t)k * nch + cc;
@@ -275,18 +306,20 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
         }
         __syncthreads();
       }
+      const long long t1 = clock64();
       grid.sync();
+      const long long t2 = clock64();
       // ---- resolution: one thread per bidder; the winner of each object applies its bid
       int* nxt = s.un[cur ^ 1];
       for (int k = gtid; k < nu; k += gthreads) {
-        const int i = un[k];
-        const int j = s.bj[k];
-        const unsigned long long kj = s.key[j];
+        const int i = ldm(&un[k]);
+        const int j = ldm(&s.bj[k]);
+        const unsigned long long kj = ldm(&s.key[j]);
         bool requeue = true;
         if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
-          const double p_old = s.price[j];
-          const double p_new = p_old + s.gam[k];
-          const int prev = s.owner[j];
+          const double p_old = ldm(&s.price[j]);
+          const double p_new = p_old + ldm(&s.gam[k]);
+          const int prev = ldm(&s.owner[j]);
           if (prev < 0 || p_new > p_old) {
             if (prev >= 0) {
               s.col4row[prev] = -1;
@@ -295,8 +328,10 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
             s.owner[j] = i;
             s.col4row[i] = j;
             s.price[j] = p_new;
-            // profit := value of the owned object at its new price -> the matched edge is tight bit-for-bit
-            s.profit[i] = s.W[(int64_t)i * s.ldw + j] - p_new;
+            // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
+            // (bval + p_old) - p_new reproduces W - p_new to rounding, keeping the matched edge tight
+            // at the 1-ulp level without re-reading W.
+            s.profit[i] = (ldm(&s.bval[k]) + p_old) - p_new;
             atomicAdd(&ctrl->progress[parity], 1);
             requeue = false;
           }
@@ -307,9 +342,15 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
       rounds++;
       bids += nu;
       bytes += (long long)nu * s.m * 8;
+      const long long t3 = clock64();
       grid.sync();
-      const int nu_next = ctrl->cnt[cur ^ 1];
-      const int prog = ctrl->progress[parity];
+      const long long t4 = clock64();
+      tph[0] += t1 - t0;
+      tph[1] += t2 - t1;
+      tph[2] += t3 - t2;
+      tph[3] += t4 - t3;
+      const int nu_next = ldm(&ctrl->cnt[cur ^ 1]);
+      const int prog = ldm(&ctrl->progress[parity]);
       if (gtid == 0) {
         ctrl->cnt[cur] = 0;            // becomes the "next" list of the coming round
         ctrl->progress[parity ^ 1] = 0;
@@ -338,6 +379,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
     s.counters->rounds += rounds;
     s.counters->bids += bids;
     s.counters->bytes += bytes;
+    for (int q = 0; q < 4; ++q) s.counters->t_phase[q] += tph[q];
   }
 }
 
@@ -515,9 +557,11 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   ctrl->stalled = 0;
   ctrl->wmin = 1.0e300;
   ctrl->wmax = -1.0e300;
+  ctrl->barrier = 0u;
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
+    for (int q = 0; q < 4; ++q) counters->t_phase[q] = 0;
   }
 }
 
@@ -557,7 +601,7 @@ constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size (sm_count * bl
 
 int pick_max_chunks(int64_t m) {
   const char* e = getenv("MCD_LAP_MIN_CHUNK");
-  int min_chunk = e ? atoi(e) : 1024;  // objects per CTA below which splitting stops paying
+  int min_chunk = e ? atoi(e) : 4096;  // objects per CTA below which splitting stops paying
   if (min_chunk < 2) min_chunk = 2;
   int64_t mc = m / min_chunk;
   if (mc < 1) mc = 1;
@@ -578,6 +622,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up(n * 8, 256);          // profit
   b += align_up(n * 4, 256);          // bj
   b += align_up(n * 8, 256);          // gam
+  b += align_up(n * 8, 256);          // bval
   b += 2 * align_up(n * 4, 256);      // un lists
   b += align_up(n * 4, 256);          // done
   b += 2 * align_up(MAX_GRID_SLOTS * 8, 256);  // pv1 pv2
@@ -614,6 +659,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.profit = reinterpret_cast<double*>(take(n * 8));
   s.bj = reinterpret_cast<int*>(take(n * 4));
   s.gam = reinterpret_cast<double*>(take(n * 8));
+  s.bval = reinterpret_cast<double*>(take(n * 8));
   s.un[0] = reinterpret_cast<int*>(take(n * 4));
   s.un[1] = reinterpret_cast<int*>(take(n * 4));
   s.done = reinterpret_cast<int*>(take(n * 4));

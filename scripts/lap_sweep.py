@@ -23,6 +23,6 @@ for st in settings:
     same = bool((a == ref[0]).all())
     print(json.dumps({"set": st, "ms_lap": round(d["ms_lap"], 2), "step_ms": [round(x, 2) for x in d["step_ms"]],
                       "rounds": d["step_rounds"], "bids": d["lap_bids"], "aug": [d["lap_aug_rows"], d["lap_aug_steps"]],
-                      "same_as_first": same, "ms_corr": round(d["ms_corr"], 2)}), flush=True)
+                      "same_as_first": same, "cyc_per_round": [round(c / max(1, sum(d["step_rounds"]))) for c in d["lap_cycles"]], "ms_corr": round(d["ms_corr"], 2)}), flush=True)
     for k in st:
         del os.environ[k]
