@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MCD_BENCH_WORKLOAD", "C5"), choices=sorted(SHAPES))
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "bf16x3"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -286,11 +286,11 @@ def main():
         q, r = divmod(M, N)
         assert np.bincount(res_dev["step"])[1:].tolist() == [N] * q + ([r] if r else [])
         flops = 2.0 * M * N * G
-        p_mma = 1 if args.precision == "fp64" else 6
+        p_mma = 1 if args.precision == "fp64" else 3
         t_corr = st["ms_corr"] * 1e-3
         t_std = st["ms_standardize"] * 1e-3
         t_lap = st["ms_lap"] * 1e-3
-        w_out = 8 if args.precision == "fp64" else 6
+        w_out = 8 if args.precision == "fp64" else 4
         std_bytes = (M / world + N) * G * (8 + w_out)
         lap_bytes_alg = sum(max(M - s * N, 0) and (min(M - s * N, N) * max(M - s * N, N) * 8.0) for s in range(nsteps))
         corr_peak = FP64_NOMINAL_TFLOPS if args.precision == "fp64" else peaks["bf16_tflops"]
@@ -311,11 +311,11 @@ def main():
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_rows", "corr": "corr_fp64_kernel" if args.precision == "fp64"
-                          else "corr_bf16x3_kernel", "lap": "lap_auction_kernel"}[dominant]
+                          else "corr_split_kernel", "lap": "lap_auction_kernel"}[dominant]
         line = {
             "metric": METRIC, "value": ms_dev * 1e-3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if args.precision == "fp64" else "bf16x3->f32", "data": "synthetic",
+            "dtype": "f64" if args.precision == "fp64" else "fp16x2-split->f32", "data": "synthetic",
             "config": {"workload": "%s: %d RNA x %d DNA x %d genes, %d steps" % (args.workload, M, N, G, nsteps),
                        "precision": args.precision, "l2": "inputs (%.1f GB) larger than L2" % ((M + N) * G * 8 / 1e9),
                        "parallelism": "rna-row-sharded corr x%d + allgather + replicated LAP" % world if world > 1

@@ -40,7 +40,7 @@ typedef enum {
 /* Arithmetic of the correlation contraction (macrodna.py:103-107). */
 typedef enum {
   MCD_PREC_FP64 = 0,  /* FP64 tensor-core (DMMA) contraction of centred rows: parity mode   */
-  MCD_PREC_BF16X3 = 1 /* tcgen05 bf16 split-precision (3 slices, 6 products), FP32 in TMEM  */
+  MCD_PREC_SPLIT_FP16 = 1 /* tcgen05 split precision: fp16 hi+lo slices, 3 products, FP32 in TMEM */
 } mcd_precision;
 
 /* Where a caller buffer lives. */
@@ -95,10 +95,11 @@ void* mcd_stream(mcd_handle h);
 int64_t mcd_padded_k(int64_t G);
 int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
                     double* centred, double* norms);
-/* Same pass, but emits three bf16 slices of the unit-norm centred row for MCD_PREC_BF16X3:
- *   slices [3, ncells, ldk16] uint16 (bf16 bits), ldk16 = mcd_padded_k_bf16(G), zero padded. */
-int64_t mcd_padded_k_bf16(int64_t G);
-int mcd_standardize_bf16x3(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
+/* Same pass, but emits the split-precision operand of MCD_PREC_SPLIT_FP16: two fp16 slices (hi, lo) of
+ * 256 * (x - mean)/||x - mean||:  slices [2, ncells, ldk16] uint16 (fp16 bits), ldk16 = mcd_padded_k_split(G),
+ * zero padded. */
+int64_t mcd_padded_k_split(int64_t G);
+int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
                            uint16_t* slices, double* norms);
 /* Synchronise and return MCD_ERR_NONFINITE if any standardise call since the last check saw NaN/Inf. */
 int mcd_check_finite(mcd_handle h);
@@ -113,8 +114,8 @@ int mcd_check_finite(mcd_handle h);
 int mcd_corr_fp64(mcd_handle h, const double* A, int64_t M, const double* B, int64_t N, int64_t G,
                   int64_t ldk, const double* nA, const double* nB, double* C, int64_t ldc,
                   double* Ct, int64_t ldct);
-/* tcgen05 split-precision variant on the bf16 slices of mcd_standardize_bf16x3. */
-int mcd_corr_bf16x3(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
+/* tcgen05 / TMEM split-precision variant on the fp16 slices of mcd_standardize_split (hi*hi + hi*lo + lo*hi). */
+int mcd_corr_split(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
                     int64_t G, int64_t ldk16, const double* nA, const double* nB, double* C,
                     int64_t ldc, double* Ct, int64_t ldct);
 

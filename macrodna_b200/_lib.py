@@ -21,7 +21,7 @@ MCD_ERR_NONFINITE = -4
 MCD_ERR_UNSUPPORTED = -5
 MCD_ERR_NOT_CONVERGED = -6
 
-PREC = {"fp64": 0, "bf16x3": 1}
+PREC = {"fp64": 0, "split": 1}
 MEM_HOST, MEM_DEVICE = 0, 1
 MAX_STEP_STATS = 64
 
@@ -69,13 +69,13 @@ SIGNATURES = {
     "mcd_synchronize": (_I, [_VP]),
     "mcd_stream": (_VP, [_VP]),
     "mcd_padded_k": (_I64, [_I64]),
-    "mcd_padded_k_bf16": (_I64, [_I64]),
+    "mcd_padded_k_split": (_I64, [_I64]),
     "mcd_num_steps": (_I64, [_I64, _I64]),
     "mcd_standardize": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
-    "mcd_standardize_bf16x3": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_standardize_split": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_check_finite": (_I, [_VP]),
     "mcd_corr_fp64": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
-    "mcd_corr_bf16x3": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
+    "mcd_corr_split": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_transpose_f64": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I64]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),

@@ -35,7 +35,7 @@ class MaCroDNA:
     frames (index = gene ids, columns = cell ids, ``:13``); ``dna_label`` has columns
     ``clone`` and ``cell`` (``:14``).  Keyword-only extras default to reference behaviour:
 
-    * ``precision``: ``"fp64"`` (parity mode, FP64 tensor pipe) or ``"bf16x3"`` (tcgen05 split precision);
+    * ``precision``: ``"fp64"`` (parity mode, FP64 tensor pipe) or ``"split"`` (tcgen05 fp16 hi/lo split precision);
     * ``clone_column``: ``"predict_clone"`` (README.md:201, CRC_data_analysis/macrodna.py:195) or
       ``"predict"`` (src/MaCroDNA/macrodna.py:198);
     * ``verbose``: print the reference's progress lines (``:95-98,120,124,147``).

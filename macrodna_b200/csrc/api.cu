@@ -117,7 +117,7 @@ int mcd_synchronize(mcd_handle h) {
 }
 
 int64_t mcd_padded_k(int64_t G) { return (G + 15) / 16 * 16; }
-int64_t mcd_padded_k_bf16(int64_t G) { return (G + 63) / 64 * 64; }
+int64_t mcd_padded_k_split(int64_t G) { return (G + 63) / 64 * 64; }
 int64_t mcd_num_steps(int64_t M, int64_t N) { return N > 0 ? (M + N - 1) / N : 0; }
 
 int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
@@ -129,13 +129,13 @@ int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, in
   return mcd_launch_standardize(h, X, ncells, G, ldx, centred, mcd_padded_k(G), nullptr, 0, norms);
 }
 
-int mcd_standardize_bf16x3(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, uint16_t* slices,
+int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, uint16_t* slices,
                            double* norms) {
   if (!h) return MCD_ERR_INVALID;
   if (!X || !slices || !norms || ncells < 0 || G < 1 || ldx < G || G > 0x7fffffff)
-    return mcd_fail(h, MCD_ERR_INVALID, "mcd_standardize_bf16x3 arguments");
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_standardize_split arguments");
   MCD_CUDA(h, cudaSetDevice(h->device));
-  return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, slices, mcd_padded_k_bf16(G), norms);
+  return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, slices, mcd_padded_k_split(G), norms);
 }
 
 int mcd_check_finite(mcd_handle h) {
@@ -159,15 +159,15 @@ int mcd_corr_fp64(mcd_handle h, const double* A, int64_t M, const double* B, int
   return mcd_launch_corr_fp64(h, A, M, B, N, ldk, nA, nB, C, ldc, Ct, ldct);
 }
 
-int mcd_corr_bf16x3(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N, int64_t G,
+int mcd_corr_split(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N, int64_t G,
                     int64_t ldk16, const double* nA, const double* nB, double* C, int64_t ldc, double* Ct,
                     int64_t ldct) {
   if (!h) return MCD_ERR_INVALID;
   if (!A3 || !B3 || !nA || !nB || (!C && !Ct) || M < 0 || N < 0 || G < 1 || ldk16 < G || (ldk16 % 64) != 0 ||
       (C && ldc < N) || (Ct && ldct < M))
-    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_bf16x3 arguments");
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_split arguments");
   MCD_CUDA(h, cudaSetDevice(h->device));
-  return mcd_launch_corr_bf16x3(h, A3, M, B3, N, ldk16, nA, nB, C, ldc, Ct, ldct);
+  return mcd_launch_corr_split(h, A3, M, B3, N, ldk16, nA, nB, C, ldc, Ct, ldct);
 }
 
 int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
@@ -495,7 +495,7 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
   if (!rna || !dna || !assign || !step || M < 1 || N < 1 || G < 1 || ld_rna < G || ld_dna < G || M > 0x3fffffff ||
       N > 0x3fffffff || G > 0x7fffffff)
     return mcd_fail(h, MCD_ERR_INVALID, "mcd_cell2cell arguments");
-  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_BF16X3)
+  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16)
     return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
   MCD_CUDA(h, cudaSetDevice(h->device));
   const int64_t launches0 = h->launches;
@@ -542,14 +542,14 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
                                    ldct)))
       return st;
   } else {
-    const int64_t ldk16 = mcd_padded_k_bf16(G);
+    const int64_t ldk16 = mcd_padded_k_split(G);
     void *pa = nullptr, *pb = nullptr;
-    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)3 * M * ldk16 * 2, &pa))) return st;
-    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)3 * N * ldk16 * 2, &pb))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)2 * M * ldk16 * 2, &pa))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)2 * N * ldk16 * 2, &pb))) return st;
     if ((st = mcd_launch_standardize(h, d_rna, M, G, ldr, nullptr, 0, (uint16_t*)pa, ldk16, (double*)pnA))) return st;
     if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, (uint16_t*)pb, ldk16, (double*)pnB))) return st;
     MCD_CUDA(h, cudaEventRecord(get_event(h, EV_STD), h->stream));
-    if ((st = mcd_launch_corr_bf16x3(h, (uint16_t*)pa, M, (uint16_t*)pb, N, ldk16, (double*)pnA, (double*)pnB, C, ldc,
+    if ((st = mcd_launch_corr_split(h, (uint16_t*)pa, M, (uint16_t*)pb, N, ldk16, (double*)pnA, (double*)pnB, C, ldc,
                                      Ct, ldct)))
       return st;
   }

@@ -1,7 +1,328 @@
-// K2 (throughput mode) -- tcgen05 / TMEM split-precision correlation contraction.  (stub: filled in next)
+// K2 (throughput mode) -- tcgen05 / TMEM split-precision correlation contraction for sm_100a.
+//
+// Replaces the RNA x DNA double loop of the reference (src/MaCroDNA/macrodna.py:103-107) with a
+// TMA-fed 5th-generation tensor-core GEMM.  Operands are the split-precision rows K1 emits:
+//   256 * unit(x - mean) = hi + lo   (two fp16 slices, 22 significant bits)
+// and each output needs three tensor-core products  hi.hi + hi.lo + lo.hi  accumulated in FP32
+// in TMEM (the dropped lo.lo term is < 2^-22).  The epilogue rescales by 2^-16 and by
+// nn / (1e-10 + nn), nn = |r_i| |d_j|, which is exactly the reference's epsilon'd denominator
+// applied to unit vectors, and writes C and/or C^T in FP64 for the assignment solver.
+//
+// Structure (one CTA per SM, persistent over 128 x 256 output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the four slice tiles
+//               A_hi/A_lo [128 x 64], B_hi/B_lo [256 x 64] per k-block into a 2-stage ring (96 KB/stage)
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
+//               12 per k-block, accumulating into one of two 256-column TMEM buffers; tcgen05.commit
+//               frees the smem stage / publishes the accumulator through mbarriers
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, FP64 scaling, stores; overlaps the
+//               next tile's MMAs thanks to the double-buffered accumulator
+#include <cuda.h>
+
 #include "mcd_internal.cuh"
 
-int mcd_launch_corr_bf16x3(mcd_context* h, const uint16_t*, int64_t, const uint16_t*, int64_t, int64_t, const double*,
-                           const double*, double*, int64_t, double*, int64_t) {
-  return mcd_fail(h, MCD_ERR_UNSUPPORTED, "bf16x3 correlation kernel not built");
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // fp16 elements = 128 bytes = one swizzle-128B row
+constexpr int STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int A_SLICE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_SLICE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_SLICE_BYTES + 2 * B_SLICE_BYTES;  // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;  // 6 warps
+constexpr int TMEM_COLS = 512;    // two 256-column FP32 accumulators
+
+// instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO = 64 x 16 B),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;            // version
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+struct TcParams {
+  int64_t M, N;
+  int num_kb;
+  int tiles_m, tiles_n;
+  const double* nA;
+  const double* nB;
+  double* C;
+  int64_t ldc;
+  double* Ct;
+  int64_t ldct;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * STAGES;
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+  }
+  if (warp == 1) {  // one warp allocates all 512 TMEM columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          tma_load_2d(st, &map_a_hi, fb, kb * BK, tm * BM);
+          tma_load_2d(st + A_SLICE_BYTES, &map_a_lo, fb, kb * BK, tm * BM);
+          tma_load_2d(st + 2 * A_SLICE_BYTES, &map_b_hi, fb, kb * BK, tn * BN);
+          tma_load_2d(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES, &map_b_lo, fb, kb * BK, tn * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          const uint64_t da_hi = make_smem_desc(st);
+          const uint64_t da_lo = make_smem_desc(st + A_SLICE_BYTES);
+          const uint64_t db_hi = make_smem_desc(st + 2 * A_SLICE_BYTES);
+          const uint64_t db_lo = make_smem_desc(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
+            umma_f16(tmem_d, da_hi + adv, db_hi + adv, IDESC, (kb | ks) != 0);
+            umma_f16(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
+            umma_f16(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
+          }
+          umma_commit(empty_bar + 8 * stage);  // smem stage free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar + 8 * acc);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)tm * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const double na = row_ok ? p.nA[row] : 0.0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t col0 = (int64_t)tn * BN + c * 32;
+        if (col0 < p.N) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int64_t col = col0 + q;
+            if (col < p.N) {
+              const double nn = na * __ldg(p.nB + col);
+              // unit-vector dot (scaled by 2^16) * nn/(1e-10+nn) == dot(xc, yc)/(1e-10 + |xc||yc|)  (macrodna.py:25)
+              const double v = (double)__uint_as_float(r[q]) * (1.0 / 65536.0) * (nn / (1e-10 + nn));
+              if (row_ok) {
+                if (p.C) p.C[row * p.ldc + col] = v;
+                if (p.Ct) p.Ct[col * p.ldct + row] = v;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D map over one fp16 slice [rows, ldk] (K-major): box = 64 elements (128 B) x box_rows, 128 B swizzle.
+bool make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t ldk, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldk * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int mcd_launch_corr_split(mcd_context* h, const uint16_t* A2, int64_t M, const uint16_t* B2, int64_t N, int64_t ldk16,
+                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct) {
+  if (M == 0 || N == 0) return MCD_OK;
+  if ((reinterpret_cast<uintptr_t>(A2) & 15) || (reinterpret_cast<uintptr_t>(B2) & 15) || (ldk16 % BK) != 0)
+    return mcd_fail(h, MCD_ERR_INVALID, "corr_split: operands must be 16-byte aligned with ldk a multiple of 64");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  if (!make_map(&ma_hi, A2, M, ldk16, BM) || !make_map(&ma_lo, A2 + M * ldk16, M, ldk16, BM) ||
+      !make_map(&mb_hi, B2, N, ldk16, BN) || !make_map(&mb_lo, B2 + N * ldk16, N, ldk16, BN))
+    return mcd_fail(h, MCD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  TcParams p;
+  p.M = M;
+  p.N = N;
+  p.num_kb = (int)(ldk16 / BK);
+  p.tiles_m = (int)((M + BM - 1) / BM);
+  p.tiles_n = (int)((N + BN - 1) / BN);
+  p.nA = nA;
+  p.nB = nB;
+  p.C = C;
+  p.ldc = ldc;
+  p.Ct = Ct;
+  p.ldct = ldct;
+  MCD_CUDA(h, cudaFuncSetAttribute(corr_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  corr_split_kernel<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  MCD_LAUNCH_CHECK(h, "corr_split_kernel");
+  return MCD_OK;
 }

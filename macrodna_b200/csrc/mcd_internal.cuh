@@ -68,7 +68,7 @@ int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int6
                            double* centred, int64_t ldk, uint16_t* slices, int64_t ldk16, double* norms);
 int mcd_launch_corr_fp64(mcd_context* h, const double* A, int64_t M, const double* B, int64_t N, int64_t ldk,
                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
-int mcd_launch_corr_bf16x3(mcd_context* h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
+int mcd_launch_corr_split(mcd_context* h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
                            int64_t ldk16, const double* nA, const double* nB, double* C, int64_t ldc, double* Ct,
                            int64_t ldct);
 

@@ -8,12 +8,12 @@
 // Layout: X is cells x genes row-major (macrodna.py:93-94 hand-off), so one cell is
 // one contiguous vector.  A group of T threads owns one row and keeps it in
 // registers between the mean pass and the norm pass, so HBM sees exactly one read
-// (8 B/element) and one write (8 B/element FP64 centred rows, or 6 B/element for the
-// three bf16 slices).  Loads/stores are 128-bit and coalesced; reductions are warp
+// (8 B/element) and one write (8 B/element FP64 centred rows, or 4 B/element for the
+// two fp16 slices of the tcgen05 path).  Loads/stores are 128-bit and coalesced; reductions are warp
 // shuffles plus one shared-memory hop.
 #include "mcd_internal.cuh"
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -40,15 +40,16 @@ __device__ __forceinline__ double group_sum(double v, double* red) {
   return s;
 }
 
-__device__ __forceinline__ void split_bf16x3(double y, uint16_t& s0, uint16_t& s1, uint16_t& s2) {
-  __nv_bfloat16 b0 = __double2bfloat16(y);
-  double r = y - (double)__bfloat162float(b0);
-  __nv_bfloat16 b1 = __double2bfloat16(r);
-  r -= (double)__bfloat162float(b1);
-  __nv_bfloat16 b2 = __double2bfloat16(r);
-  s0 = __bfloat16_as_ushort(b0);
-  s1 = __bfloat16_as_ushort(b1);
-  s2 = __bfloat16_as_ushort(b2);
+// Split-precision operand for the tcgen05 path: y (|y| <= 1, a unit-norm centred value) is scaled by
+// 2^8 and written as fp16 hi + fp16 lo (22 significant bits; the scale keeps `lo` out of the fp16
+// subnormal range for every |y| > 5e-4).  hi*hi + hi*lo + lo*hi reproduces the product to ~2^-22.
+__device__ __forceinline__ void split_fp16x2(double y, uint16_t& s0, uint16_t& s1) {
+  const double ys = y * 256.0;
+  const __half h0 = __double2half(ys);
+  const double r = ys - (double)__half2float(h0);
+  const __half h1 = __double2half(r);
+  s0 = __half_as_ushort(h0);
+  s1 = __half_as_ushort(h1);
 }
 
 // T threads per row, NV double2 per thread (row capacity 2*T*NV elements), VEC = 128-bit loads legal.
@@ -123,25 +124,22 @@ standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ld
     const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
     uint16_t* s0 = S + row * ldk16;
     uint16_t* s1 = s0 + slice_stride;
-    uint16_t* s2 = s1 + slice_stride;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int e = 2 * (t + k * T);
       if (e < G) {
-        uint16_t a0, a1, a2, b0 = 0, b1 = 0, b2 = 0;
-        split_bf16x3(v[k].x * inv, a0, a1, a2);
-        if (e + 1 < G) split_bf16x3(v[k].y * inv, b0, b1, b2);
+        uint16_t a0, a1, b0 = 0, b1 = 0;
+        split_fp16x2(v[k].x * inv, a0, a1);
+        if (e + 1 < G) split_fp16x2(v[k].y * inv, b0, b1);
         // e is even and ldk16 is a multiple of 64: 4-byte aligned pair store (pad column is zero)
         *reinterpret_cast<uint32_t*>(s0 + e) = (uint32_t)a0 | ((uint32_t)b0 << 16);
         *reinterpret_cast<uint32_t*>(s1 + e) = (uint32_t)a1 | ((uint32_t)b1 << 16);
-        *reinterpret_cast<uint32_t*>(s2 + e) = (uint32_t)a2 | ((uint32_t)b2 << 16);
       }
     }
     const int64_t g2 = (G + 1) & ~1;
     for (int64_t c = g2 + 2 * t; c < ldk16; c += 2 * T) {
       *reinterpret_cast<uint32_t*>(s0 + c) = 0u;
       *reinterpret_cast<uint32_t*>(s1 + c) = 0u;
-      *reinterpret_cast<uint32_t*>(s2 + c) = 0u;
     }
   }
 }
@@ -178,11 +176,10 @@ standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, i
   if (S != nullptr) {
     uint16_t* s0 = S + row * ldk16;
     for (int64_t e = threadIdx.x; e < ldk16; e += 512) {
-      uint16_t a0 = 0, a1 = 0, a2 = 0;
-      if (e < G) split_bf16x3((x[e] - mean) * inv, a0, a1, a2);
+      uint16_t a0 = 0, a1 = 0;
+      if (e < G) split_fp16x2((x[e] - mean) * inv, a0, a1);
       s0[e] = a0;
       s0[slice_stride + e] = a1;
-      s0[2 * slice_stride + e] = a2;
     }
   }
 }
