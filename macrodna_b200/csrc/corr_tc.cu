@@ -8,14 +8,20 @@
 // nn / (1e-10 + nn), nn = |r_i| |d_j|, which is exactly the reference's epsilon'd denominator
 // applied to unit vectors, and writes C and/or C^T in FP64 for the assignment solver.
 //
-// Structure (one CTA per SM, persistent over 128 x 256 output tiles):
+// Accuracy: the tensor core's FP32 accumulation TRUNCATES (measured here: a bias of ~2^-24.5 of the
+// running sum per tcgen05.mma, i.e. ~1e-4 absolute at 20k genes if one accumulator ran over all of K).
+// So the contraction is chunked: every CHUNK_KB k-blocks (128 genes, 24 MMAs) the MMA warp moves on to
+// the next of four 128-column TMEM accumulators, and the epilogue warps drain the finished one into
+// FP64 registers (exact summation of the chunk partials).  That holds the error at the 1e-7 level
+// (north-star gate 1e-6) independent of K.
+//
+// Structure (one CTA per SM, persistent over 128 x 128 output tiles):
 //   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the four slice tiles
-//               A_hi/A_lo [128 x 64], B_hi/B_lo [256 x 64] per k-block into a 2-stage ring (96 KB/stage)
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
-//               12 per k-block, accumulating into one of two 256-column TMEM buffers; tcgen05.commit
-//               frees the smem stage / publishes the accumulator through mbarriers
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, FP64 scaling, stores; overlaps the
-//               next tile's MMAs thanks to the double-buffered accumulator
+//               A_hi/A_lo, B_hi/B_lo [128 x 64] per k-block into a 3-stage ring (64 KB/stage)
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
+//               12 per k-block; tcgen05.commit frees the smem stage / publishes the chunk accumulator
+//   warps 2-9   continuous epilogue: tcgen05.ld 32 lanes x 32 columns, FP64 accumulation of the chunk,
+//               and at the end of the tile the reference's scaling + stores of C / C^T
 #include <cuda.h>
 
 #include "mcd_internal.cuh"
@@ -23,16 +29,20 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BN = 128;
 constexpr int BK = 64;  // fp16 elements = 128 bytes = one swizzle-128B row
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int UMMA_K = 16;
 constexpr int A_SLICE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_SLICE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_SLICE_BYTES + 2 * B_SLICE_BYTES;  // 96 KB
+constexpr int B_SLICE_BYTES = BN * BK * 2;  // 16 KB
+constexpr int STAGE_BYTES = 2 * A_SLICE_BYTES + 2 * B_SLICE_BYTES;  // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;  // 6 warps
-constexpr int TMEM_COLS = 512;    // two 256-column FP32 accumulators
+constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue
+constexpr int NUM_ACC = 4;        // TMEM accumulator ring
+constexpr int TMEM_COLS = NUM_ACC * BN;  // 512 columns
+constexpr int CHUNK_KB = 2;       // k-blocks per accumulator fill before promotion to FP64
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_COLS = BN / 2;  // columns per epilogue thread (two warps share a TMEM lane quadrant)
 
 // instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -122,12 +132,12 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barriers (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  // barriers (8 B each): full[STAGES], empty[STAGES], tmem_full[NUM_ACC], tmem_empty[NUM_ACC]; then the TMEM base slot
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + 8 * STAGES;
   const uint32_t tfull_bar = bar_base + 16 * STAGES;
-  const uint32_t tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t tempty_bar = tfull_bar + 8 * NUM_ACC;
+  const uint32_t tmem_slot = tempty_bar + 8 * NUM_ACC;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,9 +148,9 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * a, EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -187,76 +197,85 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
+      uint32_t g = 0;  // chunk counter across tiles -> accumulator ring slot and parity
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += CHUNK_KB, ++g) {
+          const uint32_t acc = g % NUM_ACC;
+          const uint32_t acc_phase = (g / NUM_ACC) & 1;
+          mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st = smem_base + stage * STAGE_BYTES;
-          const uint64_t da_hi = make_smem_desc(st);
-          const uint64_t da_lo = make_smem_desc(st + A_SLICE_BYTES);
-          const uint64_t db_hi = make_smem_desc(st + 2 * A_SLICE_BYTES);
-          const uint64_t db_lo = make_smem_desc(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES);
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          const int kb1 = min(p.num_kb, kb0 + CHUNK_KB);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = smem_base + stage * STAGE_BYTES;
+            const uint64_t da_hi = make_smem_desc(st);
+            const uint64_t da_lo = make_smem_desc(st + A_SLICE_BYTES);
+            const uint64_t db_hi = make_smem_desc(st + 2 * A_SLICE_BYTES);
+            const uint64_t db_lo = make_smem_desc(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
-            umma_f16(tmem_d, da_hi + adv, db_hi + adv, IDESC, (kb | ks) != 0);
-            umma_f16(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
-            umma_f16(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
+              umma_f16(tmem_d, da_hi + adv, db_hi + adv, IDESC, (kb != kb0 || ks != 0) ? 1u : 0u);
+              umma_f16(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
+              umma_f16(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
+            }
+            umma_commit(empty_bar + 8 * stage);  // smem stage free once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          umma_commit(empty_bar + 8 * stage);  // smem stage free once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(tfull_bar + 8 * acc);  // chunk accumulator complete
         }
-        umma_commit(tfull_bar + 8 * acc);  // accumulator complete
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    // ===================== continuous epilogue (warps 2..9) =====================
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which 64-column half of the tile
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = (int64_t)tm * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      const double na = row_ok ? p.nA[row] : 0.0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int64_t col0 = (int64_t)tn * BN + c * 32;
-        if (col0 < p.N) {
+      double tot[EPI_COLS];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int64_t col = col0 + q;
-            if (col < p.N) {
-              const double nn = na * __ldg(p.nB + col);
-              // unit-vector dot (scaled by 2^16) * nn/(1e-10+nn) == dot(xc, yc)/(1e-10 + |xc||yc|)  (macrodna.py:25)
-              const double v = (double)__uint_as_float(r[q]) * (1.0 / 65536.0) * (nn / (1e-10 + nn));
-              if (row_ok) {
-                if (p.C) p.C[row * p.ldc + col] = v;
-                if (p.Ct) p.Ct[col * p.ldct + row] = v;
-              }
-            }
+      for (int q = 0; q < EPI_COLS; ++q) tot[q] = 0.0;
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += CHUNK_KB, ++g) {
+        const uint32_t acc = g % NUM_ACC;
+        const uint32_t acc_phase = (g / NUM_ACC) & 1;
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + half * EPI_COLS;
+#pragma unroll
+        for (int c = 0; c < EPI_COLS / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 32; ++q) tot[c * 32 + q] += (double)__uint_as_float(r[q]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      }
+      // tile done: reference scaling and stores
+      const int64_t row = (int64_t)tm * BM + quad * 32 + lane;
+      if (row < p.M) {
+        const double na = p.nA[row];
+        const int64_t col0 = (int64_t)tn * BN + half * EPI_COLS;
+#pragma unroll
+        for (int q = 0; q < EPI_COLS; ++q) {
+          const int64_t col = col0 + q;
+          if (col < p.N) {
+            const double nn = na * __ldg(p.nB + col);
+            // unit-vector dot (scaled by 2^16) * nn/(1e-10+nn) == dot(xc, yc)/(1e-10 + |xc||yc|)  (macrodna.py:25)
+            const double v = tot[q] * (1.0 / 65536.0) * (nn / (1e-10 + nn));
+            if (p.C) p.C[row * p.ldc + col] = v;
+            if (p.Ct) p.Ct[col * p.ldct + row] = v;
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
     }
   }
 

@@ -59,6 +59,8 @@ struct GridBarrier {
   }
 };
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // load of inter-CTA mutable state: L2-coherent, never served from a stale L1 line
 template <typename T>
 __device__ __forceinline__ T ldm(const T* p) {
@@ -69,14 +71,19 @@ constexpr int LAP_THREADS = 256;
 constexpr int JV_THREADS = 1024;
 constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite correlations
 
+constexpr int MAX_PHASES = 48;
+
 struct LapCtrl {
   int cnt[2];       // bidder-list lengths (double buffered)
   int progress[2];  // successful bids per round (double buffered by round parity)
   int cur;          // which list is current
-  int stalled;      // phase A ended with bidders left
+  int stalled;      // phase A ended with bidders it cannot place (exact ties / guard) -> augmentation kernel
   double wmin, wmax;
-  unsigned int barrier;  // GridBarrier counter
-  int pad[1];
+  int finished;     // the final (eps = 0) phase has run: later auction launches are no-ops
+  int in_tail;      // the wide kernel stopped with <= TAIL_NU bidders: the cluster kernel continues the phase
+  int pad;
+  double eps;       // eps of the phase in flight (handed from the wide kernel to the tail kernel)
+  unsigned int barrier[MAX_PHASES];  // one GridBarrier counter per wide-kernel launch
 };
 
 struct LapState {
@@ -106,10 +113,7 @@ struct LapState {
   double* sc_val;    // [n + 1] their path cost when scanned
   LapCtrl* ctrl;
   mcd_lap_counters* counters;
-  double theta;        // eps-scaling factor (square case)
-  double eps_min_rel;  // last scaling eps relative to the cost range
   long long max_rounds;
-  int square_scaling;
 };
 
 struct Top2 {
@@ -173,29 +177,32 @@ __device__ __forceinline__ void finalize_bid(const LapState& s, int k, int i, To
   atomicMax(&s.key[j], pack_bid(gamma, i));
 }
 
-// Phase A.  One cooperative launch runs every round of every eps phase.
-__global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
-  GridBarrier grid{&s.ctrl->barrier, 0u};
+// Phase A, wide part.  One cooperative launch runs the rounds of ONE eps phase for as long as more
+// than `tail_nu` persons are bidding; the narrow remainder of the phase is handed to the cluster
+// kernel below (the bidder count never grows within a phase: every bidder either wins and evicts at
+// most one owner, or re-queues itself).  eps = eps_factor * (cost range); eps_factor == 0 is the final,
+// exact, naive phase.
+__global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
+                                                                  int tail_nu) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished) return;  // uniform: written only at the very end of earlier launches
+  const int first_phase = phase_idx == 0;
+  GridBarrier grid{&ctrl->barrier[phase_idx], 0u};
   __shared__ Top2 wred[LAP_THREADS / 32];
-  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * blockDim.x + tid;
   const int gthreads = gridDim.x * blockDim.x;
-  LapCtrl* ctrl = s.ctrl;
-
-  for (int j = gtid; j < s.m; j += gthreads) s.price[j] = 0.0;
 
   const double range = ctrl->wmax - ctrl->wmin;
-  double eps = 0.0;
-  const bool scaling = s.square_scaling && range > 0.0;
-  if (scaling) eps = range / s.theta;
+  const double eps = (eps_factor > 0.0 && range > 0.0) ? eps_factor * range : 0.0;
   long long rounds = 0, bids = 0, bytes = 0;
   long long tph[4] = {0, 0, 0, 0};
   bool guard_hit = false;
 
-  for (;;) {  // eps phases
-    // (re)start with everybody unassigned; prices are kept
+  {
+    // (re)start the phase with everybody unassigned; prices are kept from the previous phase
     for (int j = gtid; j < s.m; j += gthreads) {
+      if (first_phase) s.price[j] = 0.0;
       s.owner[j] = -1;
       s.key[j] = 0ull;
     }
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
     int nu = s.n;
     bool stalled = false;
 
-    while (nu > 0) {
+    while (nu > tail_nu) {
       if (rounds >= s.max_rounds) {
         guard_hit = true;
         break;
@@ -363,23 +370,324 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s) {
         break;
       }
     }
-    if (guard_hit || stalled || eps == 0.0) {
-      if (gtid == 0) {
-        ctrl->cur = cur;
-        ctrl->stalled = nu > 0 ? 1 : 0;
+    if (gtid == 0) {
+      ctrl->cur = cur;
+      ctrl->eps = eps;
+      const bool aborted = stalled || guard_hit;
+      if (eps == 0.0) {
+        // final phase: either done, or the cluster kernel finishes it, or the augmentation kernel must
+        ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
+        ctrl->stalled = (aborted && nu > 0) ? 1 : 0;
+        ctrl->finished = (aborted || nu == 0) ? 1 : 0;
+      } else {
+        // scaling phase: its only product is the price vector; a guard hit just ends it early
+        ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
       }
-      break;
     }
-    // next eps phase (square case only)
-    eps /= s.theta;
-    if (eps < s.eps_min_rel * range) eps = 0.0;
-    grid.sync();  // everyone has read ctrl->cnt before the phase reset rewrites it
   }
   if (gtid == 0) {
     s.counters->rounds += rounds;
     s.counters->bids += bids;
     s.counters->bytes += bytes;
     for (int q = 0; q < 4; ++q) s.counters->t_phase[q] += tph[q];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Phase A, narrow part: one thread-block cluster runs the rounds with <= TAIL_NU bidders.
+//
+// ~93 % of all rounds have a handful of bidders and are pure latency; on the whole grid a round costs
+// ~35 dependent L2 round trips + two grid barriers (~10 us).  Here the object side of the state lives in
+// DISTRIBUTED SHARED MEMORY: CTA c of the cluster owns a contiguous slice of the objects (prices +
+// owners in its smem), every CTA scans its slice of each bidder's cost row (the only global-memory
+// round trip of the round), per-CTA (best, second) partials travel to CTA 0 with st.async
+// (DSMEM store + mbarrier complete_tx: no fence, no L1 invalidate), CTA 0's first warp merges them,
+// resolves the winners and multicasts a fixed-size packet (next bidder list + price/owner updates)
+// back to every CTA the same way.  Global memory is only written behind the critical path, so the
+// wide kernel / augmentation kernel find a consistent state afterwards.
+// ------------------------------------------------------------------------------------------------
+constexpr int TAIL_NU = 32;        // max bidders per round (one warp resolves them)
+constexpr int TAIL_THREADS = 512;  // 16 warps per CTA
+constexpr int TAIL_WARPS = TAIL_THREADS / 32;
+constexpr int TAIL_MAX_CS = 16;    // largest (non-portable) cluster
+
+struct __align__(16) TailPart {  // 48 bytes
+  double v1, v2;                 // best / second-best value (W - price) in the slice
+  double p1, p2;                 // their prices
+  int j1, j2, o1, o2;            // their objects and current owners
+};
+struct __align__(16) TailPacket {  // CTA 0 -> every CTA, once per round
+  int4 ent[TAIL_NU];             // x: next-round bidder (or -1), y: updated object (or -1), z: its new owner
+  double price[TAIL_NU];         // new price of ent[t].y
+  int4 hdr;                      // x: next bidder count, y: accepted bids this round
+};
+constexpr uint32_t TAIL_PACKET_BYTES = sizeof(TailPacket);
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint64_t a, uint64_t b, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+               "l"(a), "l"(b), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b64(uint32_t raddr, uint64_t a, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(a),
+               "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4i(uint32_t raddr, int4 v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void tail_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tail_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tail_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TW_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TW_DONE;\n"
+      "bra TW_LOOP;\n"
+      "TW_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tail_merge(TailPart& a, const TailPart& b) {
+  // fold b's two candidates into a's top-2, carrying price/owner along
+  if (b.j1 >= 0 && better(b.v1, b.j1, a.v1, a.j1)) {
+    a.v2 = a.v1, a.j2 = a.j1, a.p2 = a.p1, a.o2 = a.o1;
+    a.v1 = b.v1, a.j1 = b.j1, a.p1 = b.p1, a.o1 = b.o1;
+    if (b.j2 >= 0 && better(b.v2, b.j2, a.v2, a.j2)) a.v2 = b.v2, a.j2 = b.j2, a.p2 = b.p2, a.o2 = b.o2;
+  } else if (b.j1 >= 0 && better(b.v1, b.j1, a.v2, a.j2)) {
+    a.v2 = b.v1, a.j2 = b.j1, a.p2 = b.p1, a.o2 = b.o1;
+  }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, int mc /* objects per CTA, even */) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished || !ctrl->in_tail) return;  // uniform over the cluster
+  extern __shared__ __align__(16) unsigned char tsm[];
+  uint32_t cta, ncta;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(ncta));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  // ---- shared-memory carve-up (identical in every CTA, so mapa addresses line up)
+  TailPart* cpart = reinterpret_cast<TailPart*>(tsm);                               // [TAIL_NU][TAIL_MAX_CS] (used in CTA 0)
+  TailPacket* packet = reinterpret_cast<TailPacket*>(cpart + TAIL_NU * TAIL_MAX_CS);
+  Top2* wpart = reinterpret_cast<Top2*>(packet + 1);                                // [TAIL_NU][TAIL_WARPS]
+  int* s_list = reinterpret_cast<int*>(wpart + TAIL_NU * TAIL_WARPS);               // [TAIL_NU]
+  int* s_tmp = s_list + TAIL_NU;                                                     // [TAIL_NU]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_tmp + TAIL_NU);  // barA, barB
+  double* sprice = reinterpret_cast<double*>(bars + 2);                              // [mc]
+  int* sowner = reinterpret_cast<int*>(sprice + mc);                                 // [mc]
+  const uint32_t barA = smem_addr(bars), barB = smem_addr(bars + 1);
+
+  const int o0 = min(s.m, (int)cta * mc), o1 = min(s.m, o0 + mc);
+  for (int j = o0 + tid; j < o1; j += TAIL_THREADS) {
+    sprice[j - o0] = s.price[j];
+    sowner[j - o0] = s.owner[j];
+  }
+  const int cur_list = ctrl->cur;
+  int nu = ctrl->cnt[cur_list];
+  if (tid < TAIL_NU) s_list[tid] = tid < nu ? s.un[cur_list][tid] : -1;
+  const double eps = ctrl->eps;
+  if (tid == 0) {
+    tail_mbar_init(barA, 1);
+    tail_mbar_init(barB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (cta == 0) tail_mbar_expect(barA, ncta * (uint32_t)nu * (uint32_t)sizeof(TailPart));
+    tail_mbar_expect(barB, TAIL_PACKET_BYTES);
+  }
+  // all barriers of the cluster are initialised and armed before anybody stores remotely
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  // this warp's fixed sub-slice of the CTA's objects
+  const int sw = (((o1 - o0 + TAIL_WARPS - 1) / TAIL_WARPS) + 1) & ~1;
+  const int ws = min(o1, o0 + warp * sw), we = min(o1, ws + sw);
+  long long rounds = 0, bids = 0;
+  uint32_t parity = 0;
+  int stalled = 0;
+
+  while (nu > 0) {
+    // ---- 1. every warp scans its sub-slice of every bidder's row
+    for (int b0 = 0; b0 < nu; b0 += 4) {
+      Top2 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = Top2{NEG_INF, NEG_INF, -1, -1};
+      for (int j = ws + 2 * lane; j < we; j += 64) {
+        const bool pair = (j + 1 < we);
+        double2 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (b0 + u < nu) {
+            const double* w = s.W + (int64_t)s_list[b0 + u] * s.ldw + j;
+            if (pair && s.vec) {
+              wv[u] = __ldg(reinterpret_cast<const double2*>(w));
+            } else {
+              wv[u].x = __ldg(w);
+              wv[u].y = pair ? __ldg(w + 1) : 0.0;
+            }
+          }
+        }
+        const double pa = sprice[j - o0];
+        const double pb = pair ? sprice[j - o0 + 1] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (b0 + u < nu) {
+            top2_push_seq(t[u], wv[u].x - pa, j);
+            if (pair) top2_push_seq(t[u], wv[u].y - pb, j + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + u < nu) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            Top2 r = top2_shfl(t[u], o);
+            top2_merge(t[u], r);
+          }
+          if (lane == 0) wpart[(b0 + u) * TAIL_WARPS + warp] = t[u];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 2. thread b merges the 16 warp partials of bidder b and ships the CTA partial to CTA 0
+    if (tid < nu) {
+      Top2 a = wpart[tid * TAIL_WARPS];
+#pragma unroll
+      for (int w = 1; w < TAIL_WARPS; ++w) top2_merge(a, wpart[tid * TAIL_WARPS + w]);
+      TailPart part;
+      part.v1 = a.v1, part.v2 = a.v2, part.j1 = a.j1, part.j2 = a.j2;
+      part.p1 = a.j1 >= 0 ? sprice[a.j1 - o0] : 0.0;
+      part.p2 = a.j2 >= 0 ? sprice[a.j2 - o0] : 0.0;
+      part.o1 = a.j1 >= 0 ? sowner[a.j1 - o0] : -1;
+      part.o2 = a.j2 >= 0 ? sowner[a.j2 - o0] : -1;
+      const uint32_t dst = map_to_cta(smem_addr(&cpart[tid * TAIL_MAX_CS + cta]), 0);
+      const uint32_t rbar = map_to_cta(barA, 0);
+      st_async_v2(dst, __double_as_longlong(part.v1), __double_as_longlong(part.v2), rbar);
+      st_async_v2(dst + 16, __double_as_longlong(part.p1), __double_as_longlong(part.p2), rbar);
+      st_async_v2(dst + 32, ((uint64_t)(uint32_t)part.j2 << 32) | (uint32_t)part.j1,
+                  ((uint64_t)(uint32_t)part.o2 << 32) | (uint32_t)part.o1, rbar);
+    }
+    // ---- 3. CTA 0, warp 0: merge over CTAs, resolve, multicast the round packet
+    if (cta == 0 && warp == 0) {
+      tail_mbar_wait(barA, parity);
+      const bool live = lane < nu;
+      TailPart a{NEG_INF, NEG_INF, 0.0, 0.0, -1, -1, -1, -1};
+      if (live) {
+        a = cpart[lane * TAIL_MAX_CS];
+        for (uint32_t c = 1; c < ncta; ++c) tail_merge(a, cpart[lane * TAIL_MAX_CS + c]);
+      }
+      const int i = live ? s_list[lane] : -1;
+      int j = a.j1;
+      double p_old = a.p1, bval = a.v1;
+      int prev = a.o1;
+      if (live && eps == 0.0 && a.j2 >= 0 && a.v1 == a.v2 && a.o1 >= 0 && a.o2 < 0) {  // exact tie: take the free one
+        j = a.j2, p_old = a.p2, bval = a.v2, prev = a.o2;
+      }
+      const double gamma = (a.j2 >= 0 ? (a.v1 - a.v2) : 0.0) + eps;
+      const unsigned long long key = live ? pack_bid(gamma, i) : 0ull;
+      bool win = live;
+      for (int q = 0; q < TAIL_NU; ++q) {
+        const int jq = __shfl_sync(0xffffffffu, j, q);
+        const unsigned long long kq = __shfl_sync(0xffffffffu, key, q);
+        if (q < nu && jq == j && kq > key) win = false;
+      }
+      const double p_new = p_old + gamma;
+      const bool applied = win && (prev < 0 || p_new > p_old);
+      const bool has = live && (applied ? prev >= 0 : true);
+      const int person_out = applied ? prev : i;
+      const unsigned hmask = __ballot_sync(0xffffffffu, has);
+      const int nu_next = __popc(hmask);
+      const int nacc = __popc(__ballot_sync(0xffffffffu, applied));
+      if (has) s_tmp[__popc(hmask & ((1u << lane) - 1u))] = person_out;
+      __syncwarp();
+      int4 ent;
+      ent.x = lane < nu_next ? s_tmp[lane] : -1;
+      ent.y = applied ? j : -1;
+      ent.z = i;
+      ent.w = 0;
+      if (lane == 0 && nu_next > 0 && nacc > 0)
+        tail_mbar_expect(barA, ncta * (uint32_t)nu_next * (uint32_t)sizeof(TailPart));  // arm the next round first
+      __syncwarp();
+      for (uint32_t c = 0; c < ncta; ++c) {
+        const uint32_t rbar = map_to_cta(barB, c);
+        st_async_v4i(map_to_cta(smem_addr(&packet->ent[lane]), c), ent, rbar);
+        st_async_b64(map_to_cta(smem_addr(&packet->price[lane]), c), __double_as_longlong(p_new), rbar);
+        if (lane == 0) st_async_v4i(map_to_cta(smem_addr(&packet->hdr), c), make_int4(nu_next, nacc, 0, 0), rbar);
+      }
+      // global state, off the critical path (read again only by later kernels)
+      if (applied) {
+        s.owner[j] = i;
+        s.price[j] = p_new;
+        s.col4row[i] = j;
+        s.profit[i] = (bval + p_old) - p_new;
+        if (prev >= 0) s.col4row[prev] = -1;
+      }
+      __syncwarp();  // orders this round's col4row stores before the next round's (different lanes, same warp)
+    }
+    // ---- 4. everybody: take the packet, apply the updates that fall into the own slice
+    tail_mbar_wait(barB, parity);
+    const int4 hdr = packet->hdr;
+    int4 ent = make_int4(-1, -1, -1, 0);
+    double pnew = 0.0;
+    if (tid < TAIL_NU) {
+      ent = packet->ent[tid];
+      pnew = packet->price[tid];
+    }
+    __syncthreads();  // everyone has read the packet and passed the wait before it is re-armed / overwritten
+    if (tid == 0 && hdr.x > 0 && hdr.y > 0) tail_mbar_expect(barB, TAIL_PACKET_BYTES);
+    if (tid < TAIL_NU) {
+      s_list[tid] = ent.x;
+      if (ent.y >= o0 && ent.y < o1) {
+        sprice[ent.y - o0] = pnew;
+        sowner[ent.y - o0] = ent.z;
+      }
+    }
+    rounds++;
+    bids += nu;
+    parity ^= 1;
+    nu = hdr.x;
+    __syncthreads();
+    if (hdr.y == 0 && nu > 0) {  // nobody could raise a price: exact ties -> augmentation kernel
+      stalled = 1;
+      break;
+    }
+  }
+  // no CTA may leave while peers can still address its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (cta == 0) {
+    if (tid < nu) s.un[cur_list][tid] = s_list[tid];
+    if (tid == 0) {
+      ctrl->cnt[cur_list] = nu;
+      ctrl->in_tail = 0;
+      if (eps == 0.0) {
+        ctrl->finished = 1;
+        ctrl->stalled = (stalled && nu > 0) ? 1 : 0;
+      }
+      s.counters->rounds += rounds;
+      s.counters->bids += bids;
+      s.counters->bytes += bids * (long long)s.m * 8;
+    }
   }
 }
 
@@ -557,7 +865,10 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   ctrl->stalled = 0;
   ctrl->wmin = 1.0e300;
   ctrl->wmax = -1.0e300;
-  ctrl->barrier = 0u;
+  for (int q = 0; q < MAX_PHASES; ++q) ctrl->barrier[q] = 0u;
+  ctrl->finished = 0;
+  ctrl->in_tail = 0;
+  ctrl->eps = 0.0;
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
@@ -674,17 +985,24 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.col4row = col4row;
   s.counters = d_counters;
   const char* e;
-  s.theta = (e = getenv("MCD_LAP_THETA")) ? atof(e) : 4.0;
-  if (!(s.theta > 1.0)) s.theta = 4.0;
-  s.eps_min_rel = (e = getenv("MCD_LAP_EPS_MIN")) ? atof(e) : 1e-6;
-  s.square_scaling = (n == m && n > 1) ? 1 : 0;
-  if ((e = getenv("MCD_LAP_NO_SCALING")) && atoi(e)) s.square_scaling = 0;
+  double theta = (e = getenv("MCD_LAP_THETA")) ? atof(e) : 4.0;
+  if (!(theta > 1.0)) theta = 4.0;
+  const double eps_min_rel = (e = getenv("MCD_LAP_EPS_MIN")) ? atof(e) : 1e-6;
+  bool square_scaling = (n == m && n > 1);
+  if ((e = getenv("MCD_LAP_NO_SCALING")) && atoi(e)) square_scaling = false;
   s.max_rounds = 200000 + 64 * (long long)n;
   if ((e = getenv("MCD_LAP_MAX_ROUNDS"))) s.max_rounds = atoll(e);
 
+  // eps phases: range/theta, range/theta^2, ... >= eps_min_rel * range, then the exact eps = 0 phase
+  double factors[MAX_PHASES];
+  int nphases = 0;
+  if (square_scaling)
+    for (double f = 1.0 / theta; f >= eps_min_rel && nphases < MAX_PHASES - 1; f /= theta) factors[nphases++] = f;
+  factors[nphases++] = 0.0;
+
   lap_ctrl_init_kernel<<<1, 1, 0, h->stream>>>(s.ctrl, d_counters, 0);
   MCD_LAUNCH_CHECK(h, "lap_ctrl_init_kernel");
-  if (s.square_scaling) {
+  if (square_scaling) {
     lap_minmax_kernel<<<h->sm_count * 2, 1024, 0, h->stream>>>(W, s.n, s.m, ldw, s.ctrl);
     MCD_LAUNCH_CHECK(h, "lap_minmax_kernel");
   }
@@ -695,10 +1013,48 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (want < 1) want = 1;
   int blocks = h->sm_count * (per_sm < want ? per_sm : want);
   if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
-  void* args[] = {&s};
-  MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
-                                          h->stream));
-  h->launches++;
+
+  // cluster geometry of the narrow-round kernel
+  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : TAIL_MAX_CS;
+  if (cs > TAIL_MAX_CS) cs = TAIL_MAX_CS;
+  size_t tail_smem = 0;
+  int mc = 0;
+  bool use_tail = cs >= 1;
+  if (use_tail) {
+    mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
+    tail_smem = sizeof(TailPart) * TAIL_NU * TAIL_MAX_CS + sizeof(TailPacket) + sizeof(Top2) * TAIL_NU * TAIL_WARPS +
+                2 * TAIL_NU * sizeof(int) + 16 + (size_t)mc * 12 + 64;
+    if (tail_smem > 220 * 1024) use_tail = false;  // object slice does not fit: the wide kernel runs every round
+  }
+  if (use_tail) {
+    MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    if (cs > 8) MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
+  int tail_nu = use_tail ? TAIL_NU : 0;
+
+  for (int ph = 0; ph < nphases; ++ph) {
+    double factor = factors[ph];
+    void* args[] = {&s, &factor, &ph, &tail_nu};
+    MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
+                                            h->stream));
+    h->launches++;
+    if (use_tail) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs);
+      cfg.blockDim = dim3(TAIL_THREADS);
+      cfg.dynamicSmemBytes = tail_smem;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_kernel, s, mc));
+      h->launches++;
+    }
+  }
   lap_augment_kernel<<<1, JV_THREADS, 0, h->stream>>>(s);
   MCD_LAUNCH_CHECK(h, "lap_augment_kernel");
   lap_objective_kernel<<<1, 1024, 0, h->stream>>>(W, s.n, ldw, col4row, objective, d_counters);
