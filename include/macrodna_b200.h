@@ -63,7 +63,8 @@ typedef struct {
   int64_t lap_bytes;      /* cost bytes scanned by bidding + augmentation, all steps      */
   int64_t lap_aug_rows;   /* persons finished by shortest-augmenting-path instead of bids */
   int64_t lap_aug_steps;  /* Dijkstra steps of those augmentations                        */
-  int64_t lap_cycles[4];  /* SM cycles CTA 0 spent in: bidding, barrier 1, resolution, barrier 2 */
+  int64_t lap_cycles[8];  /* SM cycles of CTA 0. wide kernel: bidding, barrier 1, resolution, barrier 2;
+                             cluster kernel: scan, wait for partials, resolve + send, wait for packet */
   double step_ms[MCD_MAX_STEP_STATS];
   int64_t step_rounds[MCD_MAX_STEP_STATS];
   int64_t step_bids[MCD_MAX_STEP_STATS];

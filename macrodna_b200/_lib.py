@@ -41,7 +41,7 @@ class McdStats(C.Structure):
         ("lap_bytes", C.c_int64),
         ("lap_aug_rows", C.c_int64),
         ("lap_aug_steps", C.c_int64),
-        ("lap_cycles", C.c_int64 * 4),
+        ("lap_cycles", C.c_int64 * 8),
         ("step_ms", C.c_double * MAX_STEP_STATS),
         ("step_rounds", C.c_int64 * MAX_STEP_STATS),
         ("step_bids", C.c_int64 * MAX_STEP_STATS),
@@ -50,7 +50,7 @@ class McdStats(C.Structure):
     def as_dict(self):
         n = min(int(self.n_steps), MAX_STEP_STATS)
         d = {k: getattr(self, k) for k, _ in self._fields_[:13]}
-        d["lap_cycles"] = [self.lap_cycles[i] for i in range(4)]
+        d["lap_cycles"] = [self.lap_cycles[i] for i in range(8)]
         d["step_ms"] = [self.step_ms[i] for i in range(n)]
         d["step_rounds"] = [self.step_rounds[i] for i in range(n)]
         d["step_bids"] = [self.step_bids[i] for i in range(n)]

@@ -466,7 +466,7 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
       stats->lap_bytes += hc[s].bytes;
       stats->lap_aug_rows += hc[s].aug_rows;
       stats->lap_aug_steps += hc[s].aug_steps;
-      for (int q = 0; q < 4; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
+      for (int q = 0; q < 8; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
       if (s < MCD_MAX_STEP_STATS) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));
@@ -595,7 +595,7 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
       stats->lap_bytes += hc[s].bytes;
       stats->lap_aug_rows += hc[s].aug_rows;
       stats->lap_aug_steps += hc[s].aug_steps;
-      for (int q = 0; q < 4; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
+      for (int q = 0; q < 8; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
       if (s < MCD_MAX_STEP_STATS) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));

@@ -412,17 +412,15 @@ constexpr int TAIL_THREADS = 512;  // 16 warps per CTA
 constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_MAX_CS = 16;    // largest (non-portable) cluster
 
-struct __align__(16) TailPart {  // 48 bytes
-  double v1, v2;                 // best / second-best value (W - price) in the slice
-  double p1, p2;                 // their prices
-  int j1, j2, o1, o2;            // their objects and current owners
+struct __align__(16) TailPart {  // 32 bytes: one CTA's best / second-best object for one bidder
+  double v1, v2;                 // values (W - price)
+  int j1, j2, pad0, pad1;        // objects
 };
-struct __align__(16) TailPacket {  // CTA 0 -> every CTA, once per round
+struct __align__(16) TailPacket {  // lives in CTA 0; every CTA pulls it over DSMEM once per round
   int4 ent[TAIL_NU];             // x: next-round bidder (or -1), y: updated object (or -1), z: its new owner
   double price[TAIL_NU];         // new price of ent[t].y
-  int4 hdr;                      // x: next bidder count, y: accepted bids this round
 };
-constexpr uint32_t TAIL_PACKET_BYTES = sizeof(TailPacket);
+constexpr uint32_t TAIL_SIGNAL_BYTES = 8;  // per round CTA 0 pushes one 8-byte header (next count, accepted bids)
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
   uint32_t r;
@@ -464,15 +462,23 @@ __device__ __forceinline__ void tail_mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-__device__ __forceinline__ void tail_merge(TailPart& a, const TailPart& b) {
-  // fold b's two candidates into a's top-2, carrying price/owner along
-  if (b.j1 >= 0 && better(b.v1, b.j1, a.v1, a.j1)) {
-    a.v2 = a.v1, a.j2 = a.j1, a.p2 = a.p1, a.o2 = a.o1;
-    a.v1 = b.v1, a.j1 = b.j1, a.p1 = b.p1, a.o1 = b.o1;
-    if (b.j2 >= 0 && better(b.v2, b.j2, a.v2, a.j2)) a.v2 = b.v2, a.j2 = b.j2, a.p2 = b.p2, a.o2 = b.o2;
-  } else if (b.j1 >= 0 && better(b.v1, b.j1, a.v2, a.j2)) {
-    a.v2 = b.v1, a.j2 = b.j1, a.p2 = b.p1, a.o2 = b.o1;
-  }
+__device__ __forceinline__ double ld_cluster_f64(uint32_t raddr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(raddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_cluster_s32(uint32_t raddr) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(raddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 ld_cluster_v4(uint32_t raddr) {
+  int4 v;
+  asm volatile("ld.shared::cluster.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(raddr)
+               : "memory");
+  return v;
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, int mc /* objects per CTA, even */) {
@@ -492,8 +498,13 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
   Top2* wpart = reinterpret_cast<Top2*>(packet + 1);                                // [TAIL_NU][TAIL_WARPS]
   int* s_list = reinterpret_cast<int*>(wpart + TAIL_NU * TAIL_WARPS);               // [TAIL_NU]
   int* s_tmp = s_list + TAIL_NU;                                                     // [TAIL_NU]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_tmp + TAIL_NU);  // barA, barB
-  double* sprice = reinterpret_cast<double*>(bars + 2);                              // [mc]
+  uint32_t* s_rpkt = reinterpret_cast<uint32_t*>(s_tmp + TAIL_NU);                   // [TAIL_MAX_CS] remote header slot
+  uint32_t* s_rbar = s_rpkt + TAIL_MAX_CS;                                           // [TAIL_MAX_CS] remote barB
+  int* s_bj = reinterpret_cast<int*>(s_rbar + TAIL_MAX_CS);                          // [TAIL_NU] bid objects (CTA 0)
+  unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(s_bj + TAIL_NU);  // [TAIL_NU] bid keys (CTA 0)
+  unsigned long long* bars = s_bkey + TAIL_NU;                                       // barA, barB, header slot, pad
+  unsigned long long* s_hdr = bars + 2;                                              // (next count) | (accepted bids) << 32
+  double* sprice = reinterpret_cast<double*>(bars + 4);                              // [mc]
   int* sowner = reinterpret_cast<int*>(sprice + mc);                                 // [mc]
   const uint32_t barA = smem_addr(bars), barB = smem_addr(bars + 1);
 
@@ -511,107 +522,119 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
     tail_mbar_init(barB, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < (int)ncta) {
+    s_rpkt[tid] = map_to_cta(smem_addr(s_hdr), tid);
+    s_rbar[tid] = map_to_cta(barB, tid);
+  }
   __syncthreads();
   if (tid == 0) {
     if (cta == 0) tail_mbar_expect(barA, ncta * (uint32_t)nu * (uint32_t)sizeof(TailPart));
-    tail_mbar_expect(barB, TAIL_PACKET_BYTES);
+    tail_mbar_expect(barB, TAIL_SIGNAL_BYTES);
   }
+  const uint32_t pkt0 = map_to_cta(smem_addr(packet), 0);          // the packet, as seen from this CTA
+  const uint32_t price0 = map_to_cta(smem_addr(sprice), 0) - 0u;   // CTA 0's slice base; other CTAs: + stride
+  const uint32_t cta_stride = map_to_cta(smem_addr(sprice), 1 % ncta) - price0;  // shared::cluster window stride
+  const uint32_t owner0 = map_to_cta(smem_addr(sowner), 0);
   // all barriers of the cluster are initialised and armed before anybody stores remotely
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-  // this warp's fixed sub-slice of the CTA's objects
-  const int sw = (((o1 - o0 + TAIL_WARPS - 1) / TAIL_WARPS) + 1) & ~1;
-  const int ws = min(o1, o0 + warp * sw), we = min(o1, ws + sw);
   long long rounds = 0, bids = 0;
   uint32_t parity = 0;
   int stalled = 0;
+  const int span = o1 - o0;
 
+  long long tq[4] = {0, 0, 0, 0};
   while (nu > 0) {
-    // ---- 1. every warp scans its sub-slice of every bidder's row
-    for (int b0 = 0; b0 < nu; b0 += 4) {
-      Top2 t[4];
+    const long long c0 = clock64();
+    // ---- 1. scan.  G warps share one bidder's slice (G = 16, 8, 4, 2, 1 for nu = 1, 2, <=4, <=8, more), so a
+    //         round costs one row-latency plus ONE warp reduction per warp whatever the bidder count.
+    int G = TAIL_WARPS;
+    while (G > 1 && G * nu > TAIL_WARPS) G >>= 1;
+    const int per_pass = TAIL_WARPS / G;
+    const int sub = (((span + G - 1) / G) + 1) & ~1;  // even sub-slice length
+    const int g = warp % G;
+    const int ws = min(o1, o0 + g * sub), we = min(o1, ws + sub);
+    for (int b = warp / G; b < nu; b += per_pass) {
+      const double* wrow = s.W + (int64_t)s_list[b] * s.ldw;
+      Top2 t{NEG_INF, NEG_INF, -1, -1};
+      int j = ws + 2 * lane;
+      if (s.vec) {
+        for (; j + 7 * 64 + 1 < we; j += 8 * 64) {  // 8 independent 128-bit loads in flight per lane
+          double2 wv[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) t[u] = Top2{NEG_INF, NEG_INF, -1, -1};
-      for (int j = ws + 2 * lane; j < we; j += 64) {
-        const bool pair = (j + 1 < we);
-        double2 wv[4];
+          for (int u = 0; u < 8; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + j + u * 64));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (b0 + u < nu) {
-            const double* w = s.W + (int64_t)s_list[b0 + u] * s.ldw + j;
-            if (pair && s.vec) {
-              wv[u] = __ldg(reinterpret_cast<const double2*>(w));
-            } else {
-              wv[u].x = __ldg(w);
-              wv[u].y = pair ? __ldg(w + 1) : 0.0;
-            }
-          }
-        }
-        const double pa = sprice[j - o0];
-        const double pb = pair ? sprice[j - o0 + 1] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (b0 + u < nu) {
-            top2_push_seq(t[u], wv[u].x - pa, j);
-            if (pair) top2_push_seq(t[u], wv[u].y - pb, j + 1);
+          for (int u = 0; u < 8; ++u) {
+            const double2 pv = *reinterpret_cast<const double2*>(sprice + (j + u * 64 - o0));
+            top2_push_seq(t, wv[u].x - pv.x, j + u * 64);
+            top2_push_seq(t, wv[u].y - pv.y, j + u * 64 + 1);
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (b0 + u < nu) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            Top2 r = top2_shfl(t[u], o);
-            top2_merge(t[u], r);
-          }
-          if (lane == 0) wpart[(b0 + u) * TAIL_WARPS + warp] = t[u];
-        }
+      for (; j < we; j += 64) {
+        const double a0 = __ldg(wrow + j) - sprice[j - o0];
+        top2_push_seq(t, a0, j);
+        if (j + 1 < we) top2_push_seq(t, __ldg(wrow + j + 1) - sprice[j + 1 - o0], j + 1);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Top2 r = top2_shfl(t, o);
+        top2_merge(t, r);
+      }
+      if (lane == 0) wpart[b * TAIL_WARPS + g] = t;
     }
     __syncthreads();
+    const long long c1 = clock64();
     // ---- 2. thread b merges the 16 warp partials of bidder b and ships the CTA partial to CTA 0
     if (tid < nu) {
       Top2 a = wpart[tid * TAIL_WARPS];
-#pragma unroll
-      for (int w = 1; w < TAIL_WARPS; ++w) top2_merge(a, wpart[tid * TAIL_WARPS + w]);
-      TailPart part;
-      part.v1 = a.v1, part.v2 = a.v2, part.j1 = a.j1, part.j2 = a.j2;
-      part.p1 = a.j1 >= 0 ? sprice[a.j1 - o0] : 0.0;
-      part.p2 = a.j2 >= 0 ? sprice[a.j2 - o0] : 0.0;
-      part.o1 = a.j1 >= 0 ? sowner[a.j1 - o0] : -1;
-      part.o2 = a.j2 >= 0 ? sowner[a.j2 - o0] : -1;
+      for (int w = 1; w < G; ++w) top2_merge(a, wpart[tid * TAIL_WARPS + w]);
       const uint32_t dst = map_to_cta(smem_addr(&cpart[tid * TAIL_MAX_CS + cta]), 0);
       const uint32_t rbar = map_to_cta(barA, 0);
-      st_async_v2(dst, __double_as_longlong(part.v1), __double_as_longlong(part.v2), rbar);
-      st_async_v2(dst + 16, __double_as_longlong(part.p1), __double_as_longlong(part.p2), rbar);
-      st_async_v2(dst + 32, ((uint64_t)(uint32_t)part.j2 << 32) | (uint32_t)part.j1,
-                  ((uint64_t)(uint32_t)part.o2 << 32) | (uint32_t)part.o1, rbar);
+      st_async_v2(dst, __double_as_longlong(a.v1), __double_as_longlong(a.v2), rbar);
+      st_async_v2(dst + 16, ((uint64_t)(uint32_t)a.j2 << 32) | (uint32_t)a.j1, 0ull, rbar);
     }
     // ---- 3. CTA 0, warp 0: merge over CTAs, resolve, multicast the round packet
     if (cta == 0 && warp == 0) {
       tail_mbar_wait(barA, parity);
+      const long long c2 = clock64();
+      tq[1] += c2 - c1;
       const bool live = lane < nu;
-      TailPart a{NEG_INF, NEG_INF, 0.0, 0.0, -1, -1, -1, -1};
+      Top2 a{NEG_INF, NEG_INF, -1, -1};
       if (live) {
-        a = cpart[lane * TAIL_MAX_CS];
-        for (uint32_t c = 1; c < ncta; ++c) tail_merge(a, cpart[lane * TAIL_MAX_CS + c]);
+        for (uint32_t c = 0; c < ncta; ++c) {
+          const TailPart& q = cpart[lane * TAIL_MAX_CS + c];
+          top2_merge(a, Top2{q.v1, q.v2, q.j1, q.j2});
+        }
+      }
+      // price / owner of the two candidates live in the owning CTA's shared memory
+      double p1 = 0.0, p2 = 0.0;
+      int own1 = -1, own2 = -1;
+      if (a.j1 >= 0) {
+        const uint32_t c = (uint32_t)(a.j1 / mc), off = (uint32_t)(a.j1 - (int)c * mc);
+        p1 = ld_cluster_f64(price0 + c * cta_stride + off * 8);
+        own1 = ld_cluster_s32(owner0 + c * cta_stride + off * 4);
+      }
+      if (a.j2 >= 0 && eps == 0.0 && a.v1 == a.v2) {
+        const uint32_t c = (uint32_t)(a.j2 / mc), off = (uint32_t)(a.j2 - (int)c * mc);
+        p2 = ld_cluster_f64(price0 + c * cta_stride + off * 8);
+        own2 = ld_cluster_s32(owner0 + c * cta_stride + off * 4);
       }
       const int i = live ? s_list[lane] : -1;
       int j = a.j1;
-      double p_old = a.p1, bval = a.v1;
-      int prev = a.o1;
-      if (live && eps == 0.0 && a.j2 >= 0 && a.v1 == a.v2 && a.o1 >= 0 && a.o2 < 0) {  // exact tie: take the free one
-        j = a.j2, p_old = a.p2, bval = a.v2, prev = a.o2;
+      double p_old = p1, bval = a.v1;
+      int prev = own1;
+      if (live && eps == 0.0 && a.j2 >= 0 && a.v1 == a.v2 && own1 >= 0 && own2 < 0) {  // exact tie: take the free one
+        j = a.j2, p_old = p2, bval = a.v2, prev = own2;
       }
       const double gamma = (a.j2 >= 0 ? (a.v1 - a.v2) : 0.0) + eps;
       const unsigned long long key = live ? pack_bid(gamma, i) : 0ull;
+      s_bj[lane] = j;
+      s_bkey[lane] = key;
+      __syncwarp();
       bool win = live;
-      for (int q = 0; q < TAIL_NU; ++q) {
-        const int jq = __shfl_sync(0xffffffffu, j, q);
-        const unsigned long long kq = __shfl_sync(0xffffffffu, key, q);
-        if (q < nu && jq == j && kq > key) win = false;
-      }
+      for (int q = 0; q < nu; ++q)
+        if (s_bj[q] == j && s_bkey[q] > key) win = false;
       const double p_new = p_old + gamma;
       const bool applied = win && (prev < 0 || p_new > p_old);
       const bool has = live && (applied ? prev >= 0 : true);
@@ -629,12 +652,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
       if (lane == 0 && nu_next > 0 && nacc > 0)
         tail_mbar_expect(barA, ncta * (uint32_t)nu_next * (uint32_t)sizeof(TailPart));  // arm the next round first
       __syncwarp();
-      for (uint32_t c = 0; c < ncta; ++c) {
-        const uint32_t rbar = map_to_cta(barB, c);
-        st_async_v4i(map_to_cta(smem_addr(&packet->ent[lane]), c), ent, rbar);
-        st_async_b64(map_to_cta(smem_addr(&packet->price[lane]), c), __double_as_longlong(p_new), rbar);
-        if (lane == 0) st_async_v4i(map_to_cta(smem_addr(&packet->hdr), c), make_int4(nu_next, nacc, 0, 0), rbar);
-      }
+      packet->ent[lane] = ent;
+      packet->price[lane] = p_new;
+      __syncwarp();
+      // one 8-byte push per CTA completes its barB; the packet itself is pulled by the receivers
+      if (lane < (int)ncta)
+        st_async_b64(s_rpkt[lane], ((uint64_t)(uint32_t)nacc << 32) | (uint32_t)nu_next, s_rbar[lane]);
       // global state, off the critical path (read again only by later kernels)
       if (applied) {
         s.owner[j] = i;
@@ -644,20 +667,25 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
         if (prev >= 0) s.col4row[prev] = -1;
       }
       __syncwarp();  // orders this round's col4row stores before the next round's (different lanes, same warp)
+      tq[2] += clock64() - c2;
     }
+    const long long c3 = clock64();
     // ---- 4. everybody: take the packet, apply the updates that fall into the own slice
     tail_mbar_wait(barB, parity);
-    const int4 hdr = packet->hdr;
+    tq[3] += clock64() - c3;
+    tq[0] += c1 - c0;
+    const unsigned long long hw = *s_hdr;
+    const int4 hdr = make_int4((int)(uint32_t)hw, (int)(uint32_t)(hw >> 32), 0, 0);
     int4 ent = make_int4(-1, -1, -1, 0);
     double pnew = 0.0;
-    if (tid < TAIL_NU) {
-      ent = packet->ent[tid];
-      pnew = packet->price[tid];
+    if (tid < nu || tid < hdr.x) {  // entries beyond max(bidders, next bidders) carry nothing
+      ent = ld_cluster_v4(pkt0 + (uint32_t)(tid * sizeof(int4)));
+      pnew = ld_cluster_f64(pkt0 + (uint32_t)(sizeof(int4) * TAIL_NU + tid * sizeof(double)));
     }
-    __syncthreads();  // everyone has read the packet and passed the wait before it is re-armed / overwritten
-    if (tid == 0 && hdr.x > 0 && hdr.y > 0) tail_mbar_expect(barB, TAIL_PACKET_BYTES);
+    __syncthreads();  // everyone is past the wait and has its entry before the barrier is re-armed
+    if (tid == 0 && hdr.x > 0 && hdr.y > 0) tail_mbar_expect(barB, TAIL_SIGNAL_BYTES);
     if (tid < TAIL_NU) {
-      s_list[tid] = ent.x;
+      s_list[tid] = tid < hdr.x ? ent.x : -1;
       if (ent.y >= o0 && ent.y < o1) {
         sprice[ent.y - o0] = pnew;
         sowner[ent.y - o0] = ent.z;
@@ -687,6 +715,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
       s.counters->rounds += rounds;
       s.counters->bids += bids;
       s.counters->bytes += bids * (long long)s.m * 8;
+      for (int q = 0; q < 4; ++q) s.counters->t_phase[4 + q] += tq[q];
     }
   }
 }
@@ -872,7 +901,7 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
-    for (int q = 0; q < 4; ++q) counters->t_phase[q] = 0;
+    for (int q = 0; q < 8; ++q) counters->t_phase[q] = 0;
   }
 }
 
@@ -1015,7 +1044,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
 
   // cluster geometry of the narrow-round kernel
-  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : TAIL_MAX_CS;
+  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? TAIL_MAX_CS : 8);
   if (cs > TAIL_MAX_CS) cs = TAIL_MAX_CS;
   size_t tail_smem = 0;
   int mc = 0;
@@ -1023,7 +1052,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (use_tail) {
     mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
     tail_smem = sizeof(TailPart) * TAIL_NU * TAIL_MAX_CS + sizeof(TailPacket) + sizeof(Top2) * TAIL_NU * TAIL_WARPS +
-                2 * TAIL_NU * sizeof(int) + 16 + (size_t)mc * 12 + 64;
+                2 * TAIL_NU * sizeof(int) + 2 * TAIL_MAX_CS * 4 + TAIL_NU * 12 + 16 + (size_t)mc * 12 + 64;
     if (tail_smem > 220 * 1024) use_tail = false;  // object slice does not fit: the wide kernel runs every round
   }
   if (use_tail) {

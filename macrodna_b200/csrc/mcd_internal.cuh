@@ -80,7 +80,8 @@ struct mcd_lap_counters {  // device-resident, one per solve
   long long aug_steps;
   int status;  // 0 ok, 1 = guard hit
   int pad;
-  long long t_phase[4];  // SM cycles seen by CTA 0: bidding, barrier 1, resolution, barrier 2
+  long long t_phase[8];  // SM cycles seen by CTA 0. wide kernel: bidding, barrier 1, resolution, barrier 2;
+                         // cluster kernel: scan, wait partials, resolve+send, wait packet
 };
 size_t mcd_lap_workspace_bytes(int64_t n, int64_t m);
 // Solve one rectangular max-assignment (n <= m).  `work` is mcd_lap_workspace_bytes(n, m) of device memory.
