@@ -129,14 +129,14 @@ class ClockSampler:
 def cpu_baseline(M, N, G, clones, budget_s=20.0):
     """Times oracle/restatement.py on sub-instances of the workload (same aspect ratio, same gene
     count) and extrapolates to the full shape: correlation linearly in M*N*G (dgemm-bound),
-    the LSA step loop by a power law in the instance scale fitted on two sub-instances."""
+    the LSA step loop by a power law in the instance scale fitted on the two largest sub-instances."""
     from macrodna_b200 import synth
     from oracle import restatement as R
 
     cores = os.cpu_count() or 1
     full_pairs = float(M) * N
 
-    def run(scale):
+    def run(scale, corr_rows=1.0):
         m, n = max(2, int(M * scale)), max(2, int(N * scale))
         inst = synth.make_arrays(m, n, G, clones, seed=77)
         t0 = time.perf_counter()
@@ -144,24 +144,26 @@ def cpu_baseline(M, N, G, clones, budget_s=20.0):
         t1 = time.perf_counter()
         R.step_loop(corrs)
         t2 = time.perf_counter()
-        return m, n, t1 - t0, t2 - t1
+        return m, n, (t1 - t0) * corr_rows, t2 - t1
 
     if full_pairs * G <= 2.5e11:  # small enough: time the whole workload
         m, n, tc, tl = run(1.0)
         return {"value": tc + tl, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "full workload %dx%dx%d: corr %.3fs (dgemm, %d threads) + LSA step loop %.3fs (1 thread)" % (
                     m, n, G, tc, cores, tl), "corr_s": tc, "lap_s": tl, "extrapolated": False}
-    s1, s2 = 0.05, 0.1
+    s0, s1, s2 = 0.05, 0.1, 0.2
+    m0, n0, tc0, tl0 = run(s0)
     m1, n1, tc1, tl1 = run(s1)
-    m2, n2, tc2, tl2 = run(s2)
-    corr_full = tc2 * (full_pairs / (m2 * n2))
+    m2, n2, _, tl2 = run(s2, corr_rows=0.25)  # LSA on the 0.2-scale instance; its dgemm on a quarter of the rows
+    corr_full = tc1 * (full_pairs / (m1 * n1))
     expo = max(2.0, np.log(max(tl2, 1e-9) / max(tl1, 1e-9)) / np.log(s2 / s1))
     lap_full = tl2 * (1.0 / s2) ** expo
     return {"value": corr_full + lap_full, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": True,
             "corr_s": corr_full, "lap_s": lap_full,
-            "sample": ("sub-instances %dx%d and %dx%d (x%d genes) of the %dx%dx%d workload: corr %.2fs/%.2fs "
-                       "(dgemm on %d threads, extrapolated linearly in M*N*G), LSA step loop %.2fs/%.2fs (1 thread, "
-                       "power law exponent %.2f in scale)") % (m1, n1, m2, n2, G, M, N, G, tc1, tc2, cores, tl1, tl2, expo)}
+            "sample": ("sub-instances %dx%d, %dx%d and %dx%d (x%d genes) of the %dx%dx%d workload: corr %.2fs at the middle "
+                       "one (dgemm on %d threads, extrapolated linearly in M*N*G); LSA step loop %.2fs/%.2fs/%.2fs "
+                       "(1 thread, power law exponent %.2f fitted on the two largest)") % (
+                m0, n0, m1, n1, m2, n2, G, M, N, G, tc1, cores, tl0, tl1, tl2, expo)}
 
 
 def run_reference_arm(args):
@@ -197,6 +199,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("MCD_BENCH_WORKLOAD", "C5"), choices=sorted(SHAPES))
     ap.add_argument("--precision", default="fp64", choices=["fp64", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="skip the companion split-precision (tcgen05) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -278,6 +281,37 @@ def main():
     h2d = rna_host.numel() * 8 + dna_host.numel() * 8
     d2h = M * 4 * 2 + res_e2e["objs"].size * 8
 
+    split = None
+    if world == 1 and args.precision == "fp64" and not args.no_split:
+        # companion run of the tcgen05 split-precision path on the same instance (same timing rules)
+        runner_s = mdist.ShardedCell2Cell(h, M, N, G, world, rank, device, precision="split")
+        ms_s, res_s, _ = timed(lambda: runner_s.run_device(rna_loc, dna), W, K)
+        # accuracy of its correlations against the FP64 path, whole matrix, on the device
+        lib = h.lib
+        import ctypes as C
+
+        c64 = torch.empty((M, N), dtype=torch.float64, device=device)
+        csp = torch.empty((M, N), dtype=torch.float64, device=device)
+        outs = [torch.empty(M, dtype=torch.int32, device=device) for _ in range(4)]
+        objs2 = [torch.empty(int(lib.mcd_num_steps(M, N)), dtype=torch.float64, device=device) for _ in range(2)]
+        for prec, cbuf, a_, s_, o_ in ((0, c64, outs[0], outs[1], objs2[0]), (1, csp, outs[2], outs[3], objs2[1])):
+            h.check(lib.mcd_cell2cell(h.h, rna_loc.data_ptr(), G, dna.data_ptr(), G, M, N, G, _lib.MEM_DEVICE, prec,
+                                      a_.data_ptr(), s_.data_ptr(), o_.data_ptr(), cbuf.data_ptr(), _lib.MEM_DEVICE,
+                                      None))
+        torch.cuda.synchronize()
+        stt = res_s["stats"]
+        flops_ = 2.0 * M * N * G
+        split = {
+            "value": ms_s * 1e-3, "unit": UNIT, "stage_ms": {k: stt[k] for k in ("ms_standardize", "ms_corr", "ms_lap")},
+            "corr_tflops": flops_ / (stt["ms_corr"] * 1e-3) / 1e12,
+            "tensor_tflops": 3 * flops_ / (stt["ms_corr"] * 1e-3) / 1e12,
+            "tensor_frac_of_measured_bf16": 3 * flops_ / (stt["ms_corr"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
+            "max_abs_dcorr_vs_fp64": float((c64 - csp).abs().max().item()),
+            "cells_assigned_differently_vs_fp64": int((outs[0] != outs[2]).sum().item()),
+            "rel_objective_gap_vs_fp64": float(((objs2[0] - objs2[1]).abs() / objs2[0].abs()).max().item()),
+        }
+        del c64, csp
+
     if rank == 0:
         st = res_dev["stats"]
         nsteps = int(st["n_steps"])
@@ -332,6 +366,8 @@ def main():
             "rooflines": rooflines,
             "objective": [float(x) for x in res_dev["objs"]],
         }
+        if split is not None:
+            line["split_precision"] = split
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(M, N, G, clones)
         print(json.dumps(line))
