@@ -6,39 +6,53 @@
 // exact LAP optimum is the ILP optimum.
 //
 // Algorithm (all FP64, exact complementary slackness -- no epsilon in the final answer):
-//   phase A  Jacobi forward auction in a persistent cooperative kernel.  Every unassigned
-//            person scans its cost row against the current prices (best, second best),
-//            bids  price += best - second  (the "naive" eps = 0 increment, which keeps
-//            exact CS: the bidder is indifferent between its object and its runner-up),
-//            one winner per object (64-bit atomicMax on (increment, person)), evicted owners
-//            rejoin the bidder list.  Long rows are split into chunks over several CTAs
-//            and merged by the last CTA to finish, so the many rounds with few bidders
-//            are latency- not single-SM-bandwidth-bound.
-//            For n == m (square, every object must be sold) the naive auction degenerates
-//            into long price wars, so it is preceded by eps-scaling phases (eps = range/4,
-//            /16, ... down to 1e-6*range); their only product is the price vector the final
-//            eps = 0 phase starts from -- valid for square problems because every object ends
-//            up assigned, so no "unassigned objects are cheapest" condition is needed.
-//            For n < m all prices start at 0 and an object once assigned stays assigned, so
-//            unassigned objects keep price 0 = the minimum: the rectangular optimality
-//            condition holds by construction.
+//   phase A  Jacobi forward auction.  Every unassigned person finds the best and second-best
+//            value  W[i,j] - price[j]  of its row, bids  price += best - second  (the "naive"
+//            eps = 0 increment, which keeps exact CS: the bidder is indifferent between its object
+//            and its runner-up), one winner per object, evicted owners rejoin the bidder list.
+//            * candidate lists: a full row sweep also keeps the person's top-128 objects and the
+//              129th value as a bound.  Prices only ever rise, so every unlisted object stays below
+//              that bound; while the list's own second-best is still >= the bound, the list's top-2
+//              ARE the row's top-2 and the bid needs 128 gathers instead of an m-long sweep
+//              (18x fewer row sweeps at 10k x 50k, identical trajectory).
+//            * wide rounds (> TAIL_NU bidders) run in a persistent cooperative kernel over the
+//              whole grid; the narrow rounds (~93 % of all rounds, a handful of bidders each) run
+//              in ONE CTA, where a round is a few hundred cycles of L1/L2 latency instead of two
+//              grid barriers.
+//            * n == m (every object must be sold) degenerates into price wars, so it is preceded by
+//              eps-scaling phases (eps = range/4, /16, ... >= 1e-6*range) whose only product is the
+//              price vector the final eps = 0 phase starts from -- valid for square problems because
+//              every object ends up assigned.  For n < m all prices start at 0 and an object once
+//              assigned stays assigned, so unassigned objects keep price 0 = the minimum: the
+//              rectangular optimality condition holds by construction.
 //   phase B  whatever the auction leaves (exact ties give zero increments -> no progress) is
-//            finished by shortest-augmenting-path (Jonker-Volgenant/Dijkstra) steps that
-//            start from the auction's dual-feasible prices/profits and tight partial matching.
+//            finished by shortest-augmenting-path (Jonker-Volgenant/Dijkstra) steps that start from
+//            the auction's dual-feasible prices/profits and tight partial matching.
 //
-// Bound: HBM/L2 bandwidth in the wide rounds (each bid reads one cost row: 8 B/object),
-// launch/sync latency in the narrow ones.
+// Bound: HBM bandwidth for the row sweeps (8 B per object), L2/launch latency for the narrow rounds.
 #include <cstdlib>
 
 #include "mcd_internal.cuh"
 
 namespace {
 
-// Grid-wide barrier for the persistent auction kernel (launched with cudaLaunchCooperativeKernel so
+constexpr int LAP_THREADS = 256;   // wide kernel CTA
+constexpr int LAP_WARPS = LAP_THREADS / 32;
+constexpr int TAIL_THREADS = 512;  // narrow kernel CTA
+constexpr int TAIL_WARPS = TAIL_THREADS / 32;
+constexpr int TAIL_NU = 128;       // bidder count at which the single-CTA kernel takes over
+constexpr int JV_THREADS = 1024;
+constexpr int LIST_K = 128;        // candidate objects kept per person
+constexpr int CAND_T = 4;          // per-thread candidates kept during a row sweep
+constexpr int MAX_PHASES = 48;
+constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size
+constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite correlations
+
+// Grid-wide barrier for the persistent wide kernel (launched with cudaLaunchCooperativeKernel so
 // all CTAs are co-resident).  One monotonic counter; each CTA's thread 0 arrives with a RELEASE
 // reduction (MEMBAR.ALL.GPU + REDG) and spins on a relaxed gpu-scope load.  There is deliberately
 // no acquire fence: on sm_100a every gpu-scope acquire (ld.acquire, fence.acq_rel, __threadfence,
-// cooperative_groups grid.sync) ends in CCTL.IVALL, a whole-L1 invalidate that ncu shows costing
+// cooperative_groups grid.sync) ends in CCTL.IVALL, a whole-L1 invalidate that ncu showed costing
 // ~4x the actual wait in this latency-bound round loop.  Instead every load of state that other
 // CTAs mutate goes through ldm() = ld.global.cg (L2, the coherence point), so there is no stale L1
 // line to drop.  The cost matrix W is immutable during the kernel and keeps the cached path.
@@ -59,19 +73,11 @@ struct GridBarrier {
   }
 };
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // load of inter-CTA mutable state: L2-coherent, never served from a stale L1 line
 template <typename T>
 __device__ __forceinline__ T ldm(const T* p) {
   return __ldcg(p);
 }
-
-constexpr int LAP_THREADS = 256;
-constexpr int JV_THREADS = 1024;
-constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite correlations
-
-constexpr int MAX_PHASES = 48;
 
 struct LapCtrl {
   int cnt[2];       // bidder-list lengths (double buffered)
@@ -80,9 +86,9 @@ struct LapCtrl {
   int stalled;      // phase A ended with bidders it cannot place (exact ties / guard) -> augmentation kernel
   double wmin, wmax;
   int finished;     // the final (eps = 0) phase has run: later auction launches are no-ops
-  int in_tail;      // the wide kernel stopped with <= TAIL_NU bidders: the cluster kernel continues the phase
-  int pad;
-  double eps;       // eps of the phase in flight (handed from the wide kernel to the tail kernel)
+  int in_tail;      // the wide kernel stopped with <= TAIL_NU bidders: the narrow kernel continues the phase
+  double eps;       // eps of the phase in flight (handed from the wide kernel to the narrow kernel)
+  int nfail[2];     // bidders whose candidate list failed this round (double buffered by round parity)
   unsigned int barrier[MAX_PHASES];  // one GridBarrier counter per wide-kernel launch
 };
 
@@ -90,27 +96,33 @@ struct LapState {
   const double* W;
   int n, m;
   int64_t ldw;
-  int max_chunks;  // upper bound on chunks per row (partial-result slots = grid size)
-  int vec;         // 128-bit loads legal
-  double* price;     // [m]
-  int* owner;        // [m]
-  unsigned long long* key;  // [m]
-  double* profit;    // [n]
-  int* col4row;      // [n]  (caller's output)
-  int* bj;           // [n] bid object per list slot
-  double* gam;       // [n] bid increment per list slot
-  double* bval;      // [n] bidder's value (W - price) of the object it bids on, per list slot
-  int* un[2];        // [n] bidder lists
-  int* done;         // [n] chunks finished per list slot
-  double* pv1;       // [grid slots] partial best
-  double* pv2;       // [grid slots] partial second
-  int* pj1;          // [grid slots]
-  int* pj2;          // [grid slots]
+  int vec;     // 128-bit loads of W rows legal
+  int list_k;  // min(LIST_K, m)
+  double* price;             // [m]
+  int* owner;                // [m]
+  unsigned long long* key;   // [m] winning bid per object in the wide kernel
+  double* profit;            // [n]
+  int* col4row;              // [n]  (caller's output)
+  int* bj;                   // [n] bid object per list slot
+  double* gam;               // [n] bid increment per list slot
+  double* bval;              // [n] bidder's value (W - price) of the object it bids on, per list slot
+  int* un[2];                // [n] bidder lists
+  int* lj;                   // [n * LIST_K] candidate objects
+  double* lw;                // [n * LIST_K] their costs W[i, j]
+  double* lbound;            // [n] no unlisted object is worth more than this to person i
+  int* lvalid;               // [n] list built
+  int* fail;                 // [n] list slots whose candidate list could not certify the top-2 this round
+  int max_chunks;            // no-list mode: upper bound on CTAs sharing one row
+  int* done;                 // [n] chunks finished per list slot
+  double* pv1;               // [grid slots] partial best / second / objects of split rows
+  double* pv2;
+  int* pj1;
+  int* pj2;
   // augmentation scratch
-  double* sp;        // [m] shortest path cost
-  int* pred;         // [m]
-  int* sc_col;       // [n + 1] scanned columns in scan order
-  double* sc_val;    // [n + 1] their path cost when scanned
+  double* sp;                // [m] shortest path cost
+  int* pred;                 // [m]
+  int* sc_col;               // [n + 1] scanned columns in scan order
+  double* sc_val;            // [n + 1] their path cost when scanned
   LapCtrl* ctrl;
   mcd_lap_counters* counters;
   long long max_rounds;
@@ -151,13 +163,17 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
   top2_push(a, b.v1, b.j1);
   top2_push(a, b.v2, b.j2);
 }
-__device__ __forceinline__ Top2 top2_shfl(const Top2& t, int o) {
-  Top2 r;
-  r.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
-  r.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
-  r.j1 = __shfl_xor_sync(0xffffffffu, t.j1, o);
-  r.j2 = __shfl_xor_sync(0xffffffffu, t.j2, o);
-  return r;
+__device__ __forceinline__ Top2 top2_warp_reduce(Top2 t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Top2 r;
+    r.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+    r.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+    r.j1 = __shfl_xor_sync(0xffffffffu, t.j1, o);
+    r.j2 = __shfl_xor_sync(0xffffffffu, t.j2, o);
+    top2_merge(t, r);
+  }
+  return t;
 }
 
 __device__ __forceinline__ unsigned long long pack_bid(double gamma, int person) {
@@ -166,8 +182,200 @@ __device__ __forceinline__ unsigned long long pack_bid(double gamma, int person)
   return ((unsigned long long)__float_as_uint(g) << 32) | (unsigned)(person + 1);
 }
 
-// Record the bid of list slot k (person i) once its whole row has been scanned.
-__device__ __forceinline__ void finalize_bid(const LapState& s, int k, int i, Top2 t, double eps) {
+// ------------------------------------------------------------------------------------------------
+// Bids from the candidate list (one warp) and from a full row sweep that rebuilds the list (one CTA)
+// ------------------------------------------------------------------------------------------------
+
+// COHERENT = true: prices / lists may have been written by other SMs in this launch (wide kernel) -> ld.cg.
+template <bool COHERENT>
+__device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top2& out) {
+  const int K = s.list_k;
+  const int* lj = s.lj + (int64_t)i * LIST_K;
+  const double* lw = s.lw + (int64_t)i * LIST_K;
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q) {
+    const int e = lane + 32 * q;
+    if (e < K) {
+      const int j = COHERENT ? ldm(lj + e) : lj[e];
+      const double w = COHERENT ? ldm(lw + e) : lw[e];
+      const double p = COHERENT ? ldm(s.price + j) : s.price[j];
+      top2_push(t, w - p, j);
+    }
+  }
+  t = top2_warp_reduce(t);
+  out = t;
+  if (K == s.m) return true;  // every object is listed
+  const double b = COHERENT ? ldm(s.lbound + i) : s.lbound[i];
+  return t.j2 >= 0 && t.v2 >= b;
+}
+
+// Whole-row sweep by an NT-thread CTA: exact top-2 of W[i,:] - price, and the person's new candidate
+// list (top list_k by current value) with its bound.  Returns the top-2 in every thread.
+// smem: cand_v[NT*CAND_T] doubles, cand_j[NT*CAND_T] ints, red[NT/32] doubles.
+template <int NT, bool COHERENT>
+__device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* cand_j, double* red) {
+  constexpr int NC = NT * CAND_T;
+  const int tid = threadIdx.x;
+  const double* w = s.W + (int64_t)i * s.ldw;
+  double tv[CAND_T];
+  int tj[CAND_T];
+#pragma unroll
+  for (int q = 0; q < CAND_T; ++q) tv[q] = NEG_INF, tj[q] = 0x7fffffff;
+  double lb = NEG_INF;  // largest value this thread dropped
+  auto push = [&](double v, int j) {
+    if (better(v, j, tv[CAND_T - 1], tj[CAND_T - 1])) {
+      lb = fmax(lb, tv[CAND_T - 1]);
+      tv[CAND_T - 1] = v;
+      tj[CAND_T - 1] = j;
+#pragma unroll
+      for (int q = CAND_T - 1; q > 0; --q) {
+        if (better(tv[q], tj[q], tv[q - 1], tj[q - 1])) {
+          const double xv = tv[q];
+          tv[q] = tv[q - 1];
+          tv[q - 1] = xv;
+          const int xj = tj[q];
+          tj[q] = tj[q - 1];
+          tj[q - 1] = xj;
+        }
+      }
+    } else {
+      lb = fmax(lb, v);
+    }
+  };
+  if (s.vec) {
+    constexpr int S = 2 * NT;
+    int j = 2 * tid;
+    for (; j + 3 * S + 1 < s.m; j += 4 * S) {  // 4 independent 128-bit loads in flight per thread
+      double2 wv[4], pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(w + j + u * S));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        pv[u] = COHERENT ? ldm(reinterpret_cast<const double2*>(s.price + j + u * S))
+                         : *reinterpret_cast<const double2*>(s.price + j + u * S);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        push(wv[u].x - pv[u].x, j + u * S);
+        push(wv[u].y - pv[u].y, j + u * S + 1);
+      }
+    }
+    for (; j < s.m; j += S) {
+      push(__ldg(w + j) - (COHERENT ? ldm(s.price + j) : s.price[j]), j);
+      if (j + 1 < s.m) push(__ldg(w + j + 1) - (COHERENT ? ldm(s.price + j + 1) : s.price[j + 1]), j + 1);
+    }
+  } else {
+    for (int j = tid; j < s.m; j += NT) push(__ldg(w + j) - (COHERENT ? ldm(s.price + j) : s.price[j]), j);
+  }
+#pragma unroll
+  for (int q = 0; q < CAND_T; ++q) {
+    cand_v[tid * CAND_T + q] = tv[q];
+    cand_j[tid * CAND_T + q] = tj[q];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lb;
+  __syncthreads();
+  // bitonic sort of the NC candidates, descending by (value, -index)
+  for (int k = 2; k <= NC; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = tid; idx < NC; idx += NT) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const double va = cand_v[idx], vb = cand_v[ixj];
+          const int ja = cand_j[idx], jb = cand_j[ixj];
+          const bool a_first = better(va, ja, vb, jb);
+          const bool desc = (idx & k) == 0;
+          if (desc ? !a_first : a_first) {
+            cand_v[idx] = vb;
+            cand_v[ixj] = va;
+            cand_j[idx] = jb;
+            cand_j[ixj] = ja;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  double bound = NEG_INF;
+#pragma unroll
+  for (int q = 0; q < NT / 32; ++q) bound = fmax(bound, red[q]);
+  const int K = s.list_k;
+  if (K < NC) bound = fmax(bound, cand_v[K]);  // (K+1)-th candidate, NEG_INF filler if there is none
+  for (int q = tid; q < K; q += NT) {
+    const int j = cand_j[q];
+    s.lj[(int64_t)i * LIST_K + q] = j;
+    s.lw[(int64_t)i * LIST_K + q] = __ldg(w + j);
+  }
+  if (tid == 0) {
+    s.lbound[i] = bound;
+    s.lvalid[i] = 1;
+  }
+  Top2 t;
+  t.v1 = cand_v[0];
+  t.j1 = cand_j[0];
+  const bool has2 = s.m > 1;
+  t.v2 = has2 ? cand_v[1] : NEG_INF;
+  t.j2 = has2 ? cand_j[1] : -1;
+  __syncthreads();  // cand_* may be reused by the caller's next sweep
+  return t;
+}
+
+
+// Plain row sweep (no candidate list): exact top-2 of W[i,:] - price by an NT-thread CTA.  Used for the
+// square (eps-scaling) problems, where every price inflates and lists would be rebuilt on every bid.
+template <int NT>
+__device__ Top2 full_scan_top2(const LapState& s, int i, Top2* wred) {
+  const int tid = threadIdx.x;
+  const double* w = s.W + (int64_t)i * s.ldw;
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  auto push = [&](double v, int j) {  // candidates arrive in increasing j per thread: strict '>' keeps ties deterministic
+    if (v > t.v1) {
+      t.v2 = t.v1, t.j2 = t.j1, t.v1 = v, t.j1 = j;
+    } else if (v > t.v2) {
+      t.v2 = v, t.j2 = j;
+    }
+  };
+  if (s.vec) {
+    constexpr int S = 2 * NT;
+    int j = 2 * tid;
+    for (; j + 3 * S + 1 < s.m; j += 4 * S) {
+      double2 wv[4], pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(w + j + u * S));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pv[u] = ldm(reinterpret_cast<const double2*>(s.price + j + u * S));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        push(wv[u].x - pv[u].x, j + u * S);
+        push(wv[u].y - pv[u].y, j + u * S + 1);
+      }
+    }
+    for (; j < s.m; j += S) {
+      push(__ldg(w + j) - ldm(s.price + j), j);
+      if (j + 1 < s.m) push(__ldg(w + j + 1) - ldm(s.price + j + 1), j + 1);
+    }
+  } else {
+    for (int j = tid; j < s.m; j += NT) push(__ldg(w + j) - ldm(s.price + j), j);
+  }
+  t = top2_warp_reduce(t);
+  if ((tid & 31) == 0) wred[tid >> 5] = t;
+  __syncthreads();
+  Top2 r = wred[0];
+#pragma unroll
+  for (int q = 1; q < NT / 32; ++q) top2_merge(r, wred[q]);
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A, wide part.  One cooperative launch runs the rounds of ONE eps phase for as long as more
+// than `tail_nu` persons are bidding; the narrow remainder of the phase is handed to the single-CTA
+// kernel below (the bidder count never grows within a phase: every bidder either wins and evicts at
+// most one owner, or re-queues itself).  eps = eps_factor * (cost range); eps_factor == 0 is the
+// final, exact, naive phase.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int i, Top2 t, double eps) {
   int j = t.j1;
   if (eps == 0.0 && t.j2 >= 0 && t.v1 == t.v2 && ldm(&s.owner[j]) >= 0 && ldm(&s.owner[t.j2]) < 0) j = t.j2;  // exact tie
   const double gamma = (t.j2 >= 0 ? (t.v1 - t.v2) : 0.0) + eps;
@@ -177,60 +385,91 @@ __device__ __forceinline__ void finalize_bid(const LapState& s, int k, int i, To
   atomicMax(&s.key[j], pack_bid(gamma, i));
 }
 
-// Phase A, wide part.  One cooperative launch runs the rounds of ONE eps phase for as long as more
-// than `tail_nu` persons are bidding; the narrow remainder of the phase is handed to the cluster
-// kernel below (the bidder count never grows within a phase: every bidder either wins and evicts at
-// most one owner, or re-queues itself).  eps = eps_factor * (cost range); eps_factor == 0 is the final,
-// exact, naive phase.
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
-                                                                  int tail_nu) {
+                                                                  int tail_nu, int use_lists) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished) return;  // uniform: written only at the very end of earlier launches
   const int first_phase = phase_idx == 0;
   GridBarrier grid{&ctrl->barrier[phase_idx], 0u};
-  __shared__ Top2 wred[LAP_THREADS / 32];
+  __shared__ double cand_v[LAP_THREADS * CAND_T];
+  __shared__ int cand_j[LAP_THREADS * CAND_T];
+  __shared__ double red[LAP_WARPS];
+  __shared__ Top2 wred[LAP_WARPS];
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   const int gtid = blockIdx.x * blockDim.x + tid;
   const int gthreads = gridDim.x * blockDim.x;
 
   const double range = ctrl->wmax - ctrl->wmin;
   const double eps = (eps_factor > 0.0 && range > 0.0) ? eps_factor * range : 0.0;
-  long long rounds = 0, bids = 0, bytes = 0;
+  long long rounds = 0, bids = 0, sweeps = 0;
   long long tph[4] = {0, 0, 0, 0};
   bool guard_hit = false;
 
-  {
-    // (re)start the phase with everybody unassigned; prices are kept from the previous phase
-    for (int j = gtid; j < s.m; j += gthreads) {
-      if (first_phase) s.price[j] = 0.0;
-      s.owner[j] = -1;
-      s.key[j] = 0ull;
-    }
-    for (int i = gtid; i < s.n; i += gthreads) {
-      s.col4row[i] = -1;
-      s.un[0][i] = i;
-      s.done[i] = 0;
-    }
-    if (gtid == 0) {
-      ctrl->cnt[0] = s.n;
-      ctrl->cnt[1] = 0;
-      ctrl->progress[0] = 0;
-      ctrl->progress[1] = 0;
-    }
-    grid.sync();
-    int cur = 0;
-    int parity = 0;
-    int nu = s.n;
-    bool stalled = false;
+  // (re)start the phase with everybody unassigned; prices (and candidate lists) are kept from the previous phase
+  for (int j = gtid; j < s.m; j += gthreads) {
+    if (first_phase) s.price[j] = 0.0;
+    s.owner[j] = -1;
+    s.key[j] = 0ull;
+  }
+  for (int i = gtid; i < s.n; i += gthreads) {
+    s.col4row[i] = -1;
+    s.un[0][i] = i;
+    s.done[i] = 0;
+    if (first_phase) s.lvalid[i] = 0;
+  }
+  if (gtid == 0) {
+    ctrl->cnt[0] = s.n;
+    ctrl->cnt[1] = 0;
+    ctrl->progress[0] = 0;
+    ctrl->progress[1] = 0;
+    ctrl->nfail[0] = 0;
+    ctrl->nfail[1] = 0;
+  }
+  grid.sync();
+  int cur = 0;
+  int parity = 0;
+  int nu = s.n;
+  bool stalled = false;
 
-    while (nu > tail_nu) {
-      if (rounds >= s.max_rounds) {
-        guard_hit = true;
-        break;
+  while (nu > tail_nu) {
+    if (rounds >= s.max_rounds) {
+      guard_hit = true;
+      break;
+    }
+    const long long t0 = clock64();
+    const int* un = s.un[cur];
+    if (use_lists) {
+      // ---- bidding, stage 1: one warp per bidder from its candidate list; failures go to a global list
+      for (int k = (blockIdx.x * LAP_WARPS + warp); k < nu; k += gridDim.x * LAP_WARPS) {
+        const int i = ldm(&un[k]);
+        bool ok = false;
+        Top2 t;
+        if (ldm(&s.lvalid[i])) ok = list_bid<true>(s, i, lane, t);
+        if (lane == 0) {
+          if (ok)
+            wide_finalize_bid(s, k, i, t, eps);
+          else
+            s.fail[atomicAdd(&ctrl->nfail[parity], 1)] = k;
+        }
       }
-      // ---- bidding: (list slot, chunk) work items over the whole grid
-      const long long t0 = clock64();
-      const int* un = s.un[cur];
+      grid.sync();
+      // ---- stage 2: one CTA per failed bidder sweeps its row and rebuilds the list (balanced over the grid)
+      const int nfail = ldm(&ctrl->nfail[parity]);
+      if (gtid == 0) ctrl->nfail[parity ^ 1] = 0;
+      for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
+        const int kk = ldm(&s.fail[f]);
+        const int i = ldm(&un[kk]);
+        const Top2 t = full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
+        if (tid == 0) {
+          wide_finalize_bid(s, kk, i, t, eps);
+          sweeps++;
+        }
+      }
+    } else {
+      // ---- bidding without lists: every bidder's row is swept; with few bidders each row is split over
+      //      ~grid/nu CTAs and merged by the last CTA to finish, so the round costs one memory latency
       // few bidders: split every row over ~grid/nu CTAs so the round costs one memory latency, not a row sweep
       int nch = 1;
       if (nu < (int)gridDim.x) nch = min(s.max_chunks, (int)gridDim.x / nu);
@@ -279,18 +518,14 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
         } else {
           for (int j = j0 + tid; j < j1; j += LAP_THREADS) top2_push_seq(t, __ldg(w + j) - ldm(&s.price[j]), j);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          Top2 r = top2_shfl(t, o);
-          top2_merge(t, r);
-        }
+        t = top2_warp_reduce(t);
         if ((tid & 31) == 0) wred[tid >> 5] = t;
         __syncthreads();
         if (tid == 0) {
 #pragma unroll
           for (int wi = 1; wi < LAP_THREADS / 32; ++wi) top2_merge(t, wred[wi]);
           if (nch == 1) {
-            finalize_bid(s, k, i, t, eps);
+            wide_finalize_bid(s, k, i, t, eps);
           } else {
             const int64_t slot = (int64_t)k * nch + c;
             s.pv1[slot] = t.v1;
@@ -307,95 +542,244 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
                 top2_merge(a, b);
               }
               s.done[k] = 0;
-              finalize_bid(s, k, i, a, eps);
+              wide_finalize_bid(s, k, i, a, eps);
             }
           }
         }
         __syncthreads();
       }
-      const long long t1 = clock64();
-      grid.sync();
-      const long long t2 = clock64();
-      // ---- resolution: one thread per bidder; the winner of each object applies its bid
-      int* nxt = s.un[cur ^ 1];
-      for (int k = gtid; k < nu; k += gthreads) {
-        const int i = ldm(&un[k]);
-        const int j = ldm(&s.bj[k]);
-        const unsigned long long kj = ldm(&s.key[j]);
-        bool requeue = true;
-        if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
-          const double p_old = ldm(&s.price[j]);
-          const double p_new = p_old + ldm(&s.gam[k]);
-          const int prev = ldm(&s.owner[j]);
-          if (prev < 0 || p_new > p_old) {
-            if (prev >= 0) {
-              s.col4row[prev] = -1;
-              nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = prev;
-            }
-            s.owner[j] = i;
-            s.col4row[i] = j;
-            s.price[j] = p_new;
-            // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
-            // (bval + p_old) - p_new reproduces W - p_new to rounding, keeping the matched edge tight
-            // at the 1-ulp level without re-reading W.
-            s.profit[i] = (ldm(&s.bval[k]) + p_old) - p_new;
-            atomicAdd(&ctrl->progress[parity], 1);
-            requeue = false;
-          }
-          s.key[j] = 0ull;
-        }
-        if (requeue) nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = i;
-      }
-      rounds++;
-      bids += nu;
-      bytes += (long long)nu * s.m * 8;
-      const long long t3 = clock64();
-      grid.sync();
-      const long long t4 = clock64();
-      tph[0] += t1 - t0;
-      tph[1] += t2 - t1;
-      tph[2] += t3 - t2;
-      tph[3] += t4 - t3;
-      const int nu_next = ldm(&ctrl->cnt[cur ^ 1]);
-      const int prog = ldm(&ctrl->progress[parity]);
-      if (gtid == 0) {
-        ctrl->cnt[cur] = 0;            // becomes the "next" list of the coming round
-        ctrl->progress[parity ^ 1] = 0;
-      }
-      cur ^= 1;
-      parity ^= 1;
-      nu = nu_next;
-      if (prog == 0 && nu > 0) {
-        stalled = true;
-        break;
-      }
+      if (blockIdx.x == 0 && tid == 0) sweeps += nu;
     }
-    if (gtid == 0) {
-      ctrl->cur = cur;
-      ctrl->eps = eps;
-      const bool aborted = stalled || guard_hit;
-      if (eps == 0.0) {
-        // final phase: either done, or the cluster kernel finishes it, or the augmentation kernel must
-        ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
-        ctrl->stalled = (aborted && nu > 0) ? 1 : 0;
-        ctrl->finished = (aborted || nu == 0) ? 1 : 0;
-      } else {
-        // scaling phase: its only product is the price vector; a guard hit just ends it early
-        ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
+    const long long t1 = clock64();
+    grid.sync();
+    const long long t2 = clock64();
+    // ---- resolution: one thread per bidder; the winner of each object applies its bid
+    int* nxt = s.un[cur ^ 1];
+    for (int k = gtid; k < nu; k += gthreads) {
+      const int i = ldm(&un[k]);
+      const int j = ldm(&s.bj[k]);
+      const unsigned long long kj = ldm(&s.key[j]);
+      bool requeue = true;
+      if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
+        const double p_old = ldm(&s.price[j]);
+        const double p_new = p_old + ldm(&s.gam[k]);
+        const int prev = ldm(&s.owner[j]);
+        if (prev < 0 || p_new > p_old) {
+          if (prev >= 0) {
+            s.col4row[prev] = -1;
+            nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = prev;
+          }
+          s.owner[j] = i;
+          s.col4row[i] = j;
+          s.price[j] = p_new;
+          // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
+          // (bval + p_old) - p_new reproduces W - p_new to rounding, keeping the matched edge tight
+          // at the 1-ulp level without re-reading W.
+          s.profit[i] = (ldm(&s.bval[k]) + p_old) - p_new;
+          atomicAdd(&ctrl->progress[parity], 1);
+          requeue = false;
+        }
+        s.key[j] = 0ull;
       }
+      if (requeue) nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = i;
+    }
+    rounds++;
+    bids += nu;
+    const long long t3 = clock64();
+    grid.sync();
+    const long long t4 = clock64();
+    tph[0] += t1 - t0;
+    tph[1] += t2 - t1;
+    tph[2] += t3 - t2;
+    tph[3] += t4 - t3;
+    const int nu_next = ldm(&ctrl->cnt[cur ^ 1]);
+    const int prog = ldm(&ctrl->progress[parity]);
+    if (gtid == 0) {
+      ctrl->cnt[cur] = 0;  // becomes the "next" list of the coming round
+      ctrl->progress[parity ^ 1] = 0;
+    }
+    cur ^= 1;
+    parity ^= 1;
+    nu = nu_next;
+    if (prog == 0 && nu > 0) {
+      stalled = true;
+      break;
     }
   }
   if (gtid == 0) {
+    ctrl->cur = cur;
+    ctrl->eps = eps;
+    const bool aborted = stalled || guard_hit;
+    if (eps == 0.0) {
+      // final phase: either done, or the narrow kernel finishes it, or the augmentation kernel must
+      ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
+      ctrl->stalled = (aborted && nu > 0) ? 1 : 0;
+      ctrl->finished = (aborted || nu == 0) ? 1 : 0;
+    } else {
+      // scaling phase: its only product is the price vector; a guard hit just ends it early
+      ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->rounds), (unsigned long long)rounds);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bids), (unsigned long long)bids);
+    for (int q = 0; q < 4; ++q) s.counters->t_phase[q] += tph[q];
+  }
+  // row sweeps are counted per CTA (thread 0 of each)
+  if (tid == 0 && sweeps > 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bytes), (unsigned long long)sweeps * s.m * 8ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A, narrow part: ONE CTA runs the rounds with <= TAIL_NU bidders.  A round is: 16 warps bid
+// from candidate lists (price gathers served by this SM's L1/L2), the few whose list fails get a
+// CTA-wide row sweep, the first TAIL_NU threads resolve winners in shared memory and apply them to
+// the global state -- which only this CTA touches for the rest of the phase, so plain loads/stores
+// ordered by __syncthreads are enough.  No grid barrier, no fence: ~1 us per round.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState s) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished || !ctrl->in_tail) return;
+  __shared__ double cand_v[TAIL_THREADS * CAND_T];
+  __shared__ int cand_j[TAIL_THREADS * CAND_T];
+  __shared__ double red[TAIL_WARPS];
+  __shared__ int s_list[2][TAIL_NU];
+  __shared__ int s_bj[TAIL_NU];
+  __shared__ double s_gam[TAIL_NU], s_bval[TAIL_NU];
+  __shared__ unsigned long long s_key[TAIL_NU];
+  __shared__ int s_fail[TAIL_NU];
+  __shared__ int s_cnt[8];  // [0] failures, [1..4] per-warp next counts, [5] accepted
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int cur_list = ctrl->cur;
+  int nu = ctrl->cnt[cur_list];
+  const double eps = ctrl->eps;
+  if (tid < TAIL_NU) s_list[0][tid] = tid < nu ? s.un[cur_list][tid] : -1;
+  __syncthreads();
+  long long rounds = 0, bids = 0, sweeps = 0;
+  long long tq[4] = {0, 0, 0, 0};
+  int cur = 0, stalled = 0;
+
+  auto finalize = [&](int b, Top2 t) {  // one thread records bidder b's bid in shared memory
+    int j = t.j1;
+    if (eps == 0.0 && t.j2 >= 0 && t.v1 == t.v2 && s.owner[j] >= 0 && s.owner[t.j2] < 0) j = t.j2;  // exact tie
+    const double gamma = (t.j2 >= 0 ? (t.v1 - t.v2) : 0.0) + eps;
+    s_bj[b] = j;
+    s_gam[b] = gamma;
+    s_bval[b] = (j == t.j1) ? t.v1 : t.v2;
+    s_key[b] = pack_bid(gamma, s_list[cur][b]);
+  };
+
+  while (nu > 0) {
+    if (rounds >= s.max_rounds) {
+      stalled = 1;
+      break;
+    }
+    const long long c0 = clock64();
+    if (tid == 0) s_cnt[0] = 0, s_cnt[5] = 0;
+    __syncthreads();
+    // ---- 1. bids from the candidate lists, one warp per bidder
+    for (int b = warp; b < nu; b += TAIL_WARPS) {
+      const int i = s_list[cur][b];
+      bool ok = false;
+      Top2 t;
+      if (s.lvalid[i]) ok = list_bid<false>(s, i, lane, t);
+      if (lane == 0) {
+        if (ok)
+          finalize(b, t);
+        else
+          s_fail[atomicAdd(&s_cnt[0], 1)] = b;
+      }
+    }
+    __syncthreads();
+    const long long c1 = clock64();
+    // ---- 2. row sweeps for the bidders whose list could not certify its top-2
+    const int nfail = s_cnt[0];
+    for (int f = 0; f < nfail; ++f) {
+      const int b = s_fail[f];
+      const Top2 t = full_scan_build<TAIL_THREADS, false>(s, s_list[cur][b], cand_v, cand_j, red);
+      if (tid == 0) finalize(b, t);
+    }
+    sweeps += nfail;
+    __syncthreads();
+    const long long c2 = clock64();
+    // ---- 3. resolution
+    int person_out = -1;
+    bool applied = false;
+    if (tid < nu) {
+      const int i = s_list[cur][tid];
+      const int j = s_bj[tid];
+      const unsigned long long key = s_key[tid];
+      bool win = true;
+      for (int q = 0; q < nu; ++q)
+        if (s_bj[q] == j && s_key[q] > key) win = false;
+      person_out = i;  // re-queue unless the bid is applied
+      if (win) {
+        const double p_old = s.price[j];
+        const double p_new = p_old + s_gam[tid];
+        const int prev = s.owner[j];
+        if (prev < 0 || p_new > p_old) {
+          applied = true;
+          person_out = prev;  // the evicted owner (or -1) bids next round
+          s.owner[j] = i;
+          s.price[j] = p_new;
+          s.col4row[i] = j;
+          s.profit[i] = (s_bval[tid] + p_old) - p_new;
+          if (prev >= 0) s.col4row[prev] = -1;
+        }
+      }
+    }
+    // ordered compaction of the next bidder list (threads 0..TAIL_NU-1 = warps 0..3)
+    if (warp < TAIL_NU / 32) {
+      const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+      const unsigned acc = __ballot_sync(0xffffffffu, applied);
+      if (lane == 0) {
+        s_cnt[1 + warp] = __popc(has);
+        atomicAdd(&s_cnt[5], __popc(acc));
+      }
+    }
+    __syncthreads();
+    int nu_next = 0;
+    for (int w = 0; w < TAIL_NU / 32; ++w) nu_next += s_cnt[1 + w];
+    if (warp < TAIL_NU / 32) {
+      int off = 0;
+      for (int w = 0; w < warp; ++w) off += s_cnt[1 + w];
+      const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+      if (person_out >= 0) s_list[cur ^ 1][off + __popc(has & ((1u << lane) - 1u))] = person_out;
+    }
+    const int accepted = s_cnt[5];
+    rounds++;
+    bids += nu;
+    __syncthreads();
+    const long long c3 = clock64();
+    tq[0] += c1 - c0;
+    tq[1] += c2 - c1;
+    tq[2] += c3 - c2;
+    cur ^= 1;
+    nu = nu_next;
+    if (accepted == 0 && nu > 0) {  // nobody could raise a price: exact ties -> augmentation kernel
+      stalled = 1;
+      break;
+    }
+  }
+  if (tid < nu) s.un[cur_list][tid] = s_list[cur][tid];
+  if (tid == 0) {
+    ctrl->cnt[cur_list] = nu;
+    ctrl->in_tail = 0;
+    if (eps == 0.0) {
+      ctrl->finished = 1;
+      ctrl->stalled = (stalled && nu > 0) ? 1 : 0;
+    }
     s.counters->rounds += rounds;
     s.counters->bids += bids;
-    s.counters->bytes += bytes;
-    for (int q = 0; q < 4; ++q) s.counters->t_phase[q] += tph[q];
+    s.counters->bytes += sweeps * (long long)s.m * 8;
+    for (int q = 0; q < 4; ++q) s.counters->t_phase[4 + q] += tq[q];
   }
 }
 
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // ------------------------------------------------------------------------------------------------
-// Phase A, narrow part: one thread-block cluster runs the rounds with <= TAIL_NU bidders.
+// Phase A, narrow part: one thread-block cluster runs the rounds with <= CL_NU bidders.
 //
 // ~93 % of all rounds have a handful of bidders and are pure latency; on the whole grid a round costs
 // ~35 dependent L2 round trips + two grid barriers (~10 us).  Here the object side of the state lives in
@@ -407,18 +791,16 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
 // back to every CTA the same way.  Global memory is only written behind the critical path, so the
 // wide kernel / augmentation kernel find a consistent state afterwards.
 // ------------------------------------------------------------------------------------------------
-constexpr int TAIL_NU = 32;        // max bidders per round (one warp resolves them)
-constexpr int TAIL_THREADS = 512;  // 16 warps per CTA
-constexpr int TAIL_WARPS = TAIL_THREADS / 32;
-constexpr int TAIL_MAX_CS = 16;    // largest (non-portable) cluster
+constexpr int CL_NU = 32;          // max bidders per round in the cluster kernel (one warp resolves them)
+constexpr int CL_MAX_CS = 16;    // largest (non-portable) cluster
 
 struct __align__(16) TailPart {  // 32 bytes: one CTA's best / second-best object for one bidder
   double v1, v2;                 // values (W - price)
   int j1, j2, pad0, pad1;        // objects
 };
 struct __align__(16) TailPacket {  // lives in CTA 0; every CTA pulls it over DSMEM once per round
-  int4 ent[TAIL_NU];             // x: next-round bidder (or -1), y: updated object (or -1), z: its new owner
-  double price[TAIL_NU];         // new price of ent[t].y
+  int4 ent[CL_NU];             // x: next-round bidder (or -1), y: updated object (or -1), z: its new owner
+  double price[CL_NU];         // new price of ent[t].y
 };
 constexpr uint32_t TAIL_SIGNAL_BYTES = 8;  // per round CTA 0 pushes one 8-byte header (next count, accepted bids)
 
@@ -481,7 +863,7 @@ __device__ __forceinline__ int4 ld_cluster_v4(uint32_t raddr) {
   return v;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, int mc /* objects per CTA, even */) {
+__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapState s, int mc /* objects per CTA, even */) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || !ctrl->in_tail) return;  // uniform over the cluster
   extern __shared__ __align__(16) unsigned char tsm[];
@@ -493,16 +875,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
   const int warp = tid >> 5;
 
   // ---- shared-memory carve-up (identical in every CTA, so mapa addresses line up)
-  TailPart* cpart = reinterpret_cast<TailPart*>(tsm);                               // [TAIL_NU][TAIL_MAX_CS] (used in CTA 0)
-  TailPacket* packet = reinterpret_cast<TailPacket*>(cpart + TAIL_NU * TAIL_MAX_CS);
-  Top2* wpart = reinterpret_cast<Top2*>(packet + 1);                                // [TAIL_NU][TAIL_WARPS]
-  int* s_list = reinterpret_cast<int*>(wpart + TAIL_NU * TAIL_WARPS);               // [TAIL_NU]
-  int* s_tmp = s_list + TAIL_NU;                                                     // [TAIL_NU]
-  uint32_t* s_rpkt = reinterpret_cast<uint32_t*>(s_tmp + TAIL_NU);                   // [TAIL_MAX_CS] remote header slot
-  uint32_t* s_rbar = s_rpkt + TAIL_MAX_CS;                                           // [TAIL_MAX_CS] remote barB
-  int* s_bj = reinterpret_cast<int*>(s_rbar + TAIL_MAX_CS);                          // [TAIL_NU] bid objects (CTA 0)
-  unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(s_bj + TAIL_NU);  // [TAIL_NU] bid keys (CTA 0)
-  unsigned long long* bars = s_bkey + TAIL_NU;                                       // barA, barB, header slot, pad
+  TailPart* cpart = reinterpret_cast<TailPart*>(tsm);                               // [CL_NU][CL_MAX_CS] (used in CTA 0)
+  TailPacket* packet = reinterpret_cast<TailPacket*>(cpart + CL_NU * CL_MAX_CS);
+  Top2* wpart = reinterpret_cast<Top2*>(packet + 1);                                // [CL_NU][TAIL_WARPS]
+  int* s_list = reinterpret_cast<int*>(wpart + CL_NU * TAIL_WARPS);               // [CL_NU]
+  int* s_tmp = s_list + CL_NU;                                                     // [CL_NU]
+  uint32_t* s_rpkt = reinterpret_cast<uint32_t*>(s_tmp + CL_NU);                   // [CL_MAX_CS] remote header slot
+  uint32_t* s_rbar = s_rpkt + CL_MAX_CS;                                           // [CL_MAX_CS] remote barB
+  int* s_bj = reinterpret_cast<int*>(s_rbar + CL_MAX_CS);                          // [CL_NU] bid objects (CTA 0)
+  unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(s_bj + CL_NU);  // [CL_NU] bid keys (CTA 0)
+  unsigned long long* bars = s_bkey + CL_NU;                                       // barA, barB, header slot, pad
   unsigned long long* s_hdr = bars + 2;                                              // (next count) | (accepted bids) << 32
   double* sprice = reinterpret_cast<double*>(bars + 4);                              // [mc]
   int* sowner = reinterpret_cast<int*>(sprice + mc);                                 // [mc]
@@ -515,7 +897,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
   }
   const int cur_list = ctrl->cur;
   int nu = ctrl->cnt[cur_list];
-  if (tid < TAIL_NU) s_list[tid] = tid < nu ? s.un[cur_list][tid] : -1;
+  if (tid < CL_NU) s_list[tid] = tid < nu ? s.un[cur_list][tid] : -1;
   const double eps = ctrl->eps;
   if (tid == 0) {
     tail_mbar_init(barA, 1);
@@ -576,11 +958,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
         top2_push_seq(t, a0, j);
         if (j + 1 < we) top2_push_seq(t, __ldg(wrow + j + 1) - sprice[j + 1 - o0], j + 1);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        Top2 r = top2_shfl(t, o);
-        top2_merge(t, r);
-      }
+      t = top2_warp_reduce(t);
       if (lane == 0) wpart[b * TAIL_WARPS + g] = t;
     }
     __syncthreads();
@@ -589,7 +967,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
     if (tid < nu) {
       Top2 a = wpart[tid * TAIL_WARPS];
       for (int w = 1; w < G; ++w) top2_merge(a, wpart[tid * TAIL_WARPS + w]);
-      const uint32_t dst = map_to_cta(smem_addr(&cpart[tid * TAIL_MAX_CS + cta]), 0);
+      const uint32_t dst = map_to_cta(smem_addr(&cpart[tid * CL_MAX_CS + cta]), 0);
       const uint32_t rbar = map_to_cta(barA, 0);
       st_async_v2(dst, __double_as_longlong(a.v1), __double_as_longlong(a.v2), rbar);
       st_async_v2(dst + 16, ((uint64_t)(uint32_t)a.j2 << 32) | (uint32_t)a.j1, 0ull, rbar);
@@ -603,7 +981,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
       Top2 a{NEG_INF, NEG_INF, -1, -1};
       if (live) {
         for (uint32_t c = 0; c < ncta; ++c) {
-          const TailPart& q = cpart[lane * TAIL_MAX_CS + c];
+          const TailPart& q = cpart[lane * CL_MAX_CS + c];
           top2_merge(a, Top2{q.v1, q.v2, q.j1, q.j2});
         }
       }
@@ -680,11 +1058,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
     double pnew = 0.0;
     if (tid < nu || tid < hdr.x) {  // entries beyond max(bidders, next bidders) carry nothing
       ent = ld_cluster_v4(pkt0 + (uint32_t)(tid * sizeof(int4)));
-      pnew = ld_cluster_f64(pkt0 + (uint32_t)(sizeof(int4) * TAIL_NU + tid * sizeof(double)));
+      pnew = ld_cluster_f64(pkt0 + (uint32_t)(sizeof(int4) * CL_NU + tid * sizeof(double)));
     }
     __syncthreads();  // everyone is past the wait and has its entry before the barrier is re-armed
     if (tid == 0 && hdr.x > 0 && hdr.y > 0) tail_mbar_expect(barB, TAIL_SIGNAL_BYTES);
-    if (tid < TAIL_NU) {
+    if (tid < CL_NU) {
       s_list[tid] = tid < hdr.x ? ent.x : -1;
       if (ent.y >= o0 && ent.y < o1) {
         sprice[ent.y - o0] = pnew;
@@ -720,7 +1098,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_kernel(LapState s, i
   }
 }
 
-// Block-wide arg-min with the (value, prefer-unowned, index) order of the augmentation step.
+// ------------------------------------------------------------------------------------------------
+// Phase B: shortest augmenting paths for the persons phase A left unassigned.  One CTA; the
+// per-step work is one cost row (m objects) spread over 1024 threads.  min-form duals:
+// u_i = -profit_i, v_j = -price_j, cost' = -W.
+// ------------------------------------------------------------------------------------------------
 struct MinItem {
   double v;
   int j;
@@ -732,9 +1114,6 @@ __device__ __forceinline__ bool min_better(const MinItem& a, const MinItem& b) {
   return a.j < b.j;
 }
 
-// Phase B: shortest augmenting paths for the persons phase A left unassigned.  One CTA; the
-// per-step work is one cost row (m objects) spread over 1024 threads.  min-form duals:
-// u_i = -profit_i, v_j = -price_j, cost' = -W.
 __global__ void __launch_bounds__(JV_THREADS) lap_augment_kernel(LapState s) {
   LapCtrl* ctrl = s.ctrl;
   if (!ctrl->stalled) return;
@@ -868,7 +1247,6 @@ __global__ void __launch_bounds__(1024) lap_minmax_kernel(const double* __restri
       hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     if (threadIdx.x == 0) {
-      // doubles of one sign order like their bit patterns; use CAS loops for generality
       unsigned long long* pmin = reinterpret_cast<unsigned long long*>(&ctrl->wmin);
       unsigned long long old = *pmin;
       while (__longlong_as_double((long long)old) > lo) {
@@ -898,6 +1276,7 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   ctrl->finished = 0;
   ctrl->in_tail = 0;
   ctrl->eps = 0.0;
+  ctrl->nfail[0] = ctrl->nfail[1] = 0;
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
@@ -937,40 +1316,27 @@ __global__ void __launch_bounds__(1024) lap_objective_kernel(const double* __res
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size (sm_count * blocks/SM)
-
-int pick_max_chunks(int64_t m) {
-  const char* e = getenv("MCD_LAP_MIN_CHUNK");
-  int min_chunk = e ? atoi(e) : 4096;  // objects per CTA below which splitting stops paying
-  if (min_chunk < 2) min_chunk = 2;
-  int64_t mc = m / min_chunk;
-  if (mc < 1) mc = 1;
-  if (mc > 256) mc = 256;
-  return (int)mc;
-}
-
 }  // namespace
 
 size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
-  const int64_t nch = 1;
-  (void)nch;
   size_t b = 0;
   b += align_up(sizeof(LapCtrl), 256);
-  b += align_up(m * 8, 256);          // price
-  b += align_up(m * 4, 256);          // owner
-  b += align_up(m * 8, 256);          // key
-  b += align_up(n * 8, 256);          // profit
-  b += align_up(n * 4, 256);          // bj
-  b += align_up(n * 8, 256);          // gam
-  b += align_up(n * 8, 256);          // bval
-  b += 2 * align_up(n * 4, 256);      // un lists
-  b += align_up(n * 4, 256);          // done
-  b += 2 * align_up(MAX_GRID_SLOTS * 8, 256);  // pv1 pv2
-  b += 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // pj1 pj2
-  b += align_up(m * 8, 256);          // sp
-  b += align_up(m * 4, 256);          // pred
-  b += align_up((n + 1) * 4, 256);    // sc_col
-  b += align_up((n + 1) * 8, 256);    // sc_val
+  b += align_up(m * 8, 256);            // price
+  b += align_up(m * 4, 256);            // owner
+  b += align_up(m * 8, 256);            // key
+  b += align_up(n * 8, 256);            // profit
+  b += align_up(n * 4, 256);            // bj
+  b += 2 * align_up(n * 8, 256);        // gam, bval
+  b += 2 * align_up(n * 4, 256);        // un lists
+  b += align_up(n * LIST_K * 4, 256);   // lj
+  b += align_up(n * LIST_K * 8, 256);   // lw
+  b += align_up(n * 8, 256);            // lbound
+  b += 3 * align_up(n * 4, 256);        // lvalid, fail, done
+  b += 2 * align_up(MAX_GRID_SLOTS * 8, 256) + 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // split-row partials
+  b += align_up(m * 8, 256);            // sp
+  b += align_up(m * 4, 256);            // pred
+  b += align_up((n + 1) * 4, 256);      // sc_col
+  b += align_up((n + 1) * 8, 256);      // sc_val
   return b;
 }
 
@@ -984,8 +1350,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.n = (int)n;
   s.m = (int)m;
   s.ldw = ldw;
-  s.max_chunks = pick_max_chunks(m);
   s.vec = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldw & 1) == 0);
+  s.list_k = (int)(m < LIST_K ? m : LIST_K);
   char* p = static_cast<char*>(work);
   auto take = [&](size_t bytes) {
     char* r = p;
@@ -1002,11 +1368,23 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.bval = reinterpret_cast<double*>(take(n * 8));
   s.un[0] = reinterpret_cast<int*>(take(n * 4));
   s.un[1] = reinterpret_cast<int*>(take(n * 4));
+  s.lj = reinterpret_cast<int*>(take(n * LIST_K * 4));
+  s.lw = reinterpret_cast<double*>(take(n * LIST_K * 8));
+  s.lbound = reinterpret_cast<double*>(take(n * 8));
+  s.lvalid = reinterpret_cast<int*>(take(n * 4));
+  s.fail = reinterpret_cast<int*>(take(n * 4));
   s.done = reinterpret_cast<int*>(take(n * 4));
   s.pv1 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
   s.pv2 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
   s.pj1 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
   s.pj2 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
+  {
+    const char* e2 = getenv("MCD_LAP_MIN_CHUNK");
+    int min_chunk = e2 ? atoi(e2) : 4096;
+    if (min_chunk < 2) min_chunk = 2;
+    int64_t mc2 = m / min_chunk;
+    s.max_chunks = (int)(mc2 < 1 ? 1 : (mc2 > 256 ? 256 : mc2));
+  }
   s.sp = reinterpret_cast<double*>(take(m * 8));
   s.pred = reinterpret_cast<int*>(take(m * 4));
   s.sc_col = reinterpret_cast<int*>(take((n + 1) * 4));
@@ -1042,32 +1420,49 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (want < 1) want = 1;
   int blocks = h->sm_count * (per_sm < want ? per_sm : want);
   if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
-
-  // cluster geometry of the narrow-round kernel
-  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? TAIL_MAX_CS : 8);
-  if (cs > TAIL_MAX_CS) cs = TAIL_MAX_CS;
+  // Mode selection.
+  //   candidate lists + single-CTA tail : n < m and rows short enough that one SM sweeps them cheaply
+  //                                       (m <= 16384) -- the list failures that remain are rare and cheap
+  //   row sweeps + cluster tail         : long rows (every sweep is spread over the grid / over 8-16 SMs of a
+  //                                       cluster), and n == m (eps-scaling inflates every price, so a list
+  //                                       would be rebuilt on almost every bid)
+  int list_max_m = (e = getenv("MCD_LAP_LIST_MAX_M")) ? atoi(e) : 16384;
+  int use_lists = (n < m && m <= list_max_m) ? 1 : 0;
+  if ((e = getenv("MCD_LAP_LISTS"))) use_lists = atoi(e) ? 1 : 0;
+  const bool list_tail = use_lists != 0;
+  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? CL_MAX_CS : 8);
+  if (cs > CL_MAX_CS) cs = CL_MAX_CS;
   size_t tail_smem = 0;
   int mc = 0;
-  bool use_tail = cs >= 1;
-  if (use_tail) {
+  bool cluster_tail = !list_tail && cs >= 1;
+  if (cluster_tail) {
     mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
-    tail_smem = sizeof(TailPart) * TAIL_NU * TAIL_MAX_CS + sizeof(TailPacket) + sizeof(Top2) * TAIL_NU * TAIL_WARPS +
-                2 * TAIL_NU * sizeof(int) + 2 * TAIL_MAX_CS * 4 + TAIL_NU * 12 + 16 + (size_t)mc * 12 + 64;
-    if (tail_smem > 220 * 1024) use_tail = false;  // object slice does not fit: the wide kernel runs every round
+    tail_smem = sizeof(TailPart) * CL_NU * CL_MAX_CS + sizeof(TailPacket) + sizeof(Top2) * CL_NU * TAIL_WARPS +
+                2 * CL_NU * sizeof(int) + 2 * CL_MAX_CS * 4 + CL_NU * 12 + 32 + (size_t)mc * 12 + 64;
+    if (tail_smem > 220 * 1024) cluster_tail = false;  // object slice does not fit: the wide kernel runs every round
   }
-  if (use_tail) {
-    MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    if (cs > 8) MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (cluster_tail) {
+    MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tail_smem));
+    if (cs > 8)
+      MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
-  int tail_nu = use_tail ? TAIL_NU : 0;
+  int tail_nu = list_tail ? TAIL_NU : (cluster_tail ? CL_NU : 0);
+  if ((e = getenv("MCD_LAP_TAIL_NU"))) {
+    const int v = atoi(e);
+    if (v >= 0 && v < tail_nu) tail_nu = v;
+  }
 
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
-    void* args[] = {&s, &factor, &ph, &tail_nu};
+    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                             h->stream));
     h->launches++;
-    if (use_tail) {
+    if (tail_nu > 0 && list_tail) {
+      lap_tail_list_kernel<<<1, TAIL_THREADS, 0, h->stream>>>(s);
+      MCD_LAUNCH_CHECK(h, "lap_tail_list_kernel");
+    } else if (tail_nu > 0 && cluster_tail) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(cs);
       cfg.blockDim = dim3(TAIL_THREADS);
@@ -1080,7 +1475,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_kernel, s, mc));
+      MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_cluster_kernel, s, mc));
       h->launches++;
     }
   }
