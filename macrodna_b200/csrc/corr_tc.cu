@@ -317,14 +317,16 @@ bool make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t ldk,
 
 }  // namespace
 
-int mcd_launch_corr_split(mcd_context* h, const uint16_t* A2, int64_t M, const uint16_t* B2, int64_t N, int64_t ldk16,
-                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct) {
+int mcd_launch_corr_split(mcd_context* h, const uint16_t* A2, const uint16_t* A_lo, int64_t M, const uint16_t* B2,
+                          const uint16_t* B_lo, int64_t N, int64_t ldk16, const double* nA, const double* nB, double* C,
+                          int64_t ldc, double* Ct, int64_t ldct) {
   if (M == 0 || N == 0) return MCD_OK;
-  if ((reinterpret_cast<uintptr_t>(A2) & 15) || (reinterpret_cast<uintptr_t>(B2) & 15) || (ldk16 % BK) != 0)
+  if ((reinterpret_cast<uintptr_t>(A2) & 15) || (reinterpret_cast<uintptr_t>(B2) & 15) ||
+      (reinterpret_cast<uintptr_t>(A_lo) & 15) || (reinterpret_cast<uintptr_t>(B_lo) & 15) || (ldk16 % BK) != 0)
     return mcd_fail(h, MCD_ERR_INVALID, "corr_split: operands must be 16-byte aligned with ldk a multiple of 64");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (!make_map(&ma_hi, A2, M, ldk16, BM) || !make_map(&ma_lo, A2 + M * ldk16, M, ldk16, BM) ||
-      !make_map(&mb_hi, B2, N, ldk16, BN) || !make_map(&mb_lo, B2 + N * ldk16, N, ldk16, BN))
+  if (!make_map(&ma_hi, A2, M, ldk16, BM) || !make_map(&ma_lo, A_lo, M, ldk16, BM) ||
+      !make_map(&mb_hi, B2, N, ldk16, BN) || !make_map(&mb_lo, B_lo, N, ldk16, BN))
     return mcd_fail(h, MCD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TcParams p;
   p.M = M;

@@ -56,7 +56,7 @@ __device__ __forceinline__ void split_fp16x2(double y, uint16_t& s0, uint16_t& s
 template <int T, int NV, bool VEC>
 __global__ void __launch_bounds__((T > 512 ? T : 512), 1)
 standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ldx, double* __restrict__ Y,
-                 int64_t ldk, uint16_t* __restrict__ S, int64_t ldk16, int64_t slice_stride,
+                 int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
                  double* __restrict__ norms, int* __restrict__ flags) {
   constexpr int BLOCK = (T > 512 ? T : 512);
   constexpr int ROWS = BLOCK / T;
@@ -123,7 +123,7 @@ standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ld
   if (S != nullptr) {
     const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
     uint16_t* s0 = S + row * ldk16;
-    uint16_t* s1 = s0 + slice_stride;
+    uint16_t* s1 = S_lo + row * ldk16;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int e = 2 * (t + k * T);
@@ -148,7 +148,7 @@ standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ld
 // (the row stays L2-resident between sweeps; declared as a 3-read variant in DESIGN.md).
 __global__ void __launch_bounds__(512)
 standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, int64_t ldx, double* __restrict__ Y,
-                      int64_t ldk, uint16_t* __restrict__ S, int64_t ldk16, int64_t slice_stride,
+                      int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
                       double* __restrict__ norms, int* __restrict__ flags) {
   __shared__ double red[16];
   const int64_t row = blockIdx.x;
@@ -175,28 +175,28 @@ standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, i
   }
   if (S != nullptr) {
     uint16_t* s0 = S + row * ldk16;
+    uint16_t* s1 = S_lo + row * ldk16;
     for (int64_t e = threadIdx.x; e < ldk16; e += 512) {
       uint16_t a0 = 0, a1 = 0;
       if (e < G) split_fp16x2((x[e] - mean) * inv, a0, a1);
       s0[e] = a0;
-      s0[slice_stride + e] = a1;
+      s1[e] = a1;
     }
   }
 }
 
 template <int T, int NV>
 int launch_t(mcd_context* h, bool vec, const double* X, int64_t ncells, int G, int64_t ldx, double* Y, int64_t ldk,
-             uint16_t* S, int64_t ldk16, double* norms) {
+             uint16_t* S, uint16_t* S_lo, int64_t ldk16, double* norms) {
   constexpr int BLOCK = (T > 512 ? T : 512);
   constexpr int ROWS = BLOCK / T;
   const int64_t grid = (ncells + ROWS - 1) / ROWS;
-  const int64_t stride = ncells * ldk16;
   if (vec)
-    standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, ldk16, stride,
+    standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, S_lo, ldk16,
                                                                           norms, h->d_flags);
   else
-    standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, ldk16,
-                                                                           stride, norms, h->d_flags);
+    standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, S_lo, ldk16,
+                                                                           norms, h->d_flags);
   MCD_LAUNCH_CHECK(h, "standardize_rows");
   return MCD_OK;
 }
@@ -204,20 +204,20 @@ int launch_t(mcd_context* h, bool vec, const double* X, int64_t ncells, int G, i
 }  // namespace
 
 int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
-                           int64_t ldk, uint16_t* slices, int64_t ldk16, double* norms) {
+                           int64_t ldk, uint16_t* slices, uint16_t* slices_lo, int64_t ldk16, double* norms) {
   if (ncells == 0) return MCD_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const int g = (int)G;
-  if (G <= 256) return launch_t<32, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 1024) return launch_t<128, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 4096) return launch_t<512, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 8192) return launch_t<512, 8>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 12288) return launch_t<512, 12>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 16384) return launch_t<512, 16>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 20480) return launch_t<512, 20>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  if (G <= 24576) return launch_t<512, 24>(h, vec, X, ncells, g, ldx, centred, ldk, slices, ldk16, norms);
-  standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, ncells, G, ldx, centred, ldk, slices, ldk16,
-                                                                ncells * ldk16, norms, h->d_flags);
+  if (G <= 256) return launch_t<32, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 1024) return launch_t<128, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 4096) return launch_t<512, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 8192) return launch_t<512, 8>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 12288) return launch_t<512, 12>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 16384) return launch_t<512, 16>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 20480) return launch_t<512, 20>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 24576) return launch_t<512, 24>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, ncells, G, ldx, centred, ldk, slices, slices_lo,
+                                                                ldk16, norms, h->d_flags);
   MCD_LAUNCH_CHECK(h, "standardize_rows_long");
   return MCD_OK;
 }
