@@ -182,7 +182,9 @@ int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw
   // counters live in the first 256 bytes of the slot
   mcd_lap_counters* cnt = static_cast<mcd_lap_counters*>(work);
   MCD_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(mcd_lap_counters), h->stream));
-  return mcd_launch_lap(h, W, n, m, ldw, col4row, objective, static_cast<char*>(work) + 256, cnt);
+  int st2 = mcd_launch_lap(h, W, n, m, ldw, col4row, objective, static_cast<char*>(work) + 256, cnt, true);
+  if (st2) return st2;
+  return mcd_check_finite(h);
 }
 
 }  // extern "C"
@@ -325,7 +327,7 @@ StepPlan plan_steps(int64_t M, int64_t N) {
 // Device outputs: d_assign[M], d_step[M], d_obj[nsteps], d_counters[nsteps].
 int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M,
                       int64_t N, int* d_assign, int* d_step, double* d_obj, mcd_lap_counters* d_counters,
-                      size_t ev_base) {
+                      size_t ev_base, bool check_finite) {
   const StepPlan plan = plan_steps(M, N);
   void* wbuf = nullptr;
   void* lapbuf = nullptr;
@@ -364,7 +366,8 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
         MCD_LAUNCH_CHECK(h, "gather_cols_kernel");
         Wp = W;
       }
-      if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s))) return st;
+      if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0)))
+        return st;
       record_dna_major_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(col4row, (int)N, act[cur], d_assign,
                                                                                  d_step, flag, (int)(s + 1));
       MCD_LAUNCH_CHECK(h, "record_dna_major_kernel");
@@ -387,7 +390,8 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
         MCD_LAUNCH_CHECK(h, "gather_rows_kernel");
         Wp = W;
       }
-      if ((st = mcd_launch_lap(h, Wp, R, N, ldw, col4row, d_obj + s, lapbuf, d_counters + s))) return st;
+      if ((st = mcd_launch_lap(h, Wp, R, N, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0)))
+        return st;
       record_rna_major_kernel<<<(unsigned)((R + 255) / 256), 256, 0, h->stream>>>(col4row, (int)R, act[cur], d_assign,
                                                                                  d_step, flag, (int)(s + 1));
       MCD_LAUNCH_CHECK(h, "record_rna_major_kernel");
@@ -447,7 +451,7 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
   const int64_t launches0 = h->launches;
   const size_t EV_LAP = 8;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
-  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP))) return st;
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP, true))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
 
   const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -455,8 +459,12 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
   MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)M * 4, kind, h->stream));
   if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
   std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  int flag = 0;
   MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the correlation matrix");
   int bad = 0;
   if (stats) memset(stats, 0, sizeof *stats);
   for (int64_t s = 0; s < nsteps; ++s) {
@@ -557,7 +565,7 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
   if (st) return st;
   int64_t rows_per = ((M + nchunk - 1) / nchunk + 127) / 128 * 128;
   if (rows_per < 128) rows_per = 128;
-  const size_t EV_CHUNK = 100;  // 3 events per chunk
+  const size_t EV_CHUNK = 100;  // 4 events per chunk: copy done, K1 start, K1 end, K2 end
   int nchunk_used = 0;
   if (in_space == MCD_MEM_HOST) MCD_CUDA(h, cudaStreamWaitEvent(h->copy_stream, get_event(h, EV_T0), 0));
   for (int64_t r0 = 0; r0 < M; r0 += rows_per, ++nchunk_used) {
@@ -567,27 +575,28 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
       double* dst = const_cast<double*>(d_rna) + r0 * G;
       MCD_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)G * 8, rna + r0 * ld_rna, (size_t)ld_rna * 8, (size_t)G * 8, (size_t)mr,
                                     cudaMemcpyHostToDevice, h->copy_stream));
-      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 3 * c), h->copy_stream));
-      MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(h, EV_CHUNK + 3 * c), 0));
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c), h->copy_stream));
+      MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(h, EV_CHUNK + 4 * c), 0));
     } else {
-      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 3 * c), h->stream));
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c), h->stream));
     }
+    MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 1), h->stream));
     const double* xr = d_rna + r0 * ldr;
     if (precision == MCD_PREC_FP64) {
       double* ac = (double*)pa + r0 * ldk;
       if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, ac, ldk, nullptr, nullptr, 0, nA + r0))) return st;
-      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 3 * c + 1), h->stream));
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
       if ((st = mcd_launch_corr_fp64(h, ac, mr, (double*)pb, N, ldk, nA + r0, nB, C + r0 * ldc, ldc, Ct + r0, ldct)))
         return st;
     } else {
       if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, nullptr, 0, a_hi + r0 * ldk, a_lo + r0 * ldk, ldk, nA + r0)))
         return st;
-      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 3 * c + 1), h->stream));
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
       if ((st = mcd_launch_corr_split(h, a_hi + r0 * ldk, a_lo + r0 * ldk, mr, b_hi, b_lo, N, ldk, nA + r0, nB,
                                       C + r0 * ldc, ldc, Ct + r0, ldct)))
         return st;
     }
-    MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 3 * c + 2), h->stream));
+    MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 3), h->stream));
   }
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_STD), h->stream));
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CORR), h->stream));
@@ -603,7 +612,7 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
   int* d_step = reinterpret_cast<int*>(mb + mi);
   double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
   mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
-  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP))) return st;
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP, false))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_LAPEND), h->stream));
 
   // ---- outputs
@@ -652,8 +661,8 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
     // ms_h2d is the EXPOSED copy time: everything of [T0, last K2] that is neither K1 nor K2.
     double k1 = 0.0, k2 = 0.0;
     for (int c = 0; c < nchunk_used; ++c) {
-      k1 += el((int)EV_CHUNK + 3 * c, (int)EV_CHUNK + 3 * c + 1);
-      k2 += el((int)EV_CHUNK + 3 * c + 1, (int)EV_CHUNK + 3 * c + 2);
+      k1 += el((int)EV_CHUNK + 4 * c + 1, (int)EV_CHUNK + 4 * c + 2);
+      k2 += el((int)EV_CHUNK + 4 * c + 2, (int)EV_CHUNK + 4 * c + 3);
     }
     const double span = el(EV_T0, EV_CORR);
     stats->ms_standardize = k1;

@@ -125,6 +125,7 @@ struct LapState {
   double* sc_val;            // [n + 1] their path cost when scanned
   LapCtrl* ctrl;
   mcd_lap_counters* counters;
+  const int* flags;  // [0] != 0: non-finite data was seen upstream -> every solver kernel is a no-op
   long long max_rounds;
 };
 
@@ -388,7 +389,7 @@ __device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int 
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
                                                                   int tail_nu, int use_lists) {
   LapCtrl* ctrl = s.ctrl;
-  if (ctrl->finished) return;  // uniform: written only at the very end of earlier launches
+  if (ctrl->finished || s.flags[0]) return;  // uniform: written only at the very end of earlier launches
   const int first_phase = phase_idx == 0;
   GridBarrier grid{&ctrl->barrier[phase_idx], 0u};
   __shared__ double cand_v[LAP_THREADS * CAND_T];
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState s) {
   LapCtrl* ctrl = s.ctrl;
-  if (ctrl->finished || !ctrl->in_tail) return;
+  if (ctrl->finished || !ctrl->in_tail || s.flags[0]) return;
   __shared__ double cand_v[TAIL_THREADS * CAND_T];
   __shared__ int cand_j[TAIL_THREADS * CAND_T];
   __shared__ double red[TAIL_WARPS];
@@ -865,7 +866,7 @@ __device__ __forceinline__ int4 ld_cluster_v4(uint32_t raddr) {
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapState s, int mc /* objects per CTA, even */) {
   LapCtrl* ctrl = s.ctrl;
-  if (ctrl->finished || !ctrl->in_tail) return;  // uniform over the cluster
+  if (ctrl->finished || !ctrl->in_tail || s.flags[0]) return;  // uniform over the cluster
   extern __shared__ __align__(16) unsigned char tsm[];
   uint32_t cta, ncta;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
@@ -1116,7 +1117,7 @@ __device__ __forceinline__ bool min_better(const MinItem& a, const MinItem& b) {
 
 __global__ void __launch_bounds__(JV_THREADS) lap_augment_kernel(LapState s) {
   LapCtrl* ctrl = s.ctrl;
-  if (!ctrl->stalled) return;
+  if (!ctrl->stalled || s.flags[0]) return;
   __shared__ MinItem red[JV_THREADS / 32];
   __shared__ MinItem best;
   const int tid = threadIdx.x;
@@ -1219,15 +1220,18 @@ __global__ void __launch_bounds__(JV_THREADS) lap_augment_kernel(LapState s) {
 }
 
 __global__ void __launch_bounds__(1024) lap_minmax_kernel(const double* __restrict__ W, int n, int m, int64_t ldw,
-                                                          LapCtrl* ctrl) {
+                                                          LapCtrl* ctrl, int* flags) {
   __shared__ double smin[32], smax[32];
   double lo = 1.0e300, hi = -1.0e300;
   const int64_t total = (int64_t)n * m;
+  bool bad = false;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const double v = W[(e / m) * ldw + (e % m)];
+    bad |= !isfinite(v);
     lo = fmin(lo, v);
     hi = fmax(hi, v);
   }
+  if (bad) atomicOr(flags, 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -1341,7 +1345,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
 }
 
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
-                   double* objective, void* work, mcd_lap_counters* d_counters) {
+                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite) {
   if (n <= 0) return MCD_OK;
   if (n > m) return mcd_fail(h, MCD_ERR_INVALID, "lap: rows must be the smaller side");
   if (m > 0x3fffffff) return mcd_fail(h, MCD_ERR_UNSUPPORTED, "lap: too many objects");
@@ -1391,6 +1395,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.sc_val = reinterpret_cast<double*>(take((n + 1) * 8));
   s.col4row = col4row;
   s.counters = d_counters;
+  s.flags = h->d_flags;
   const char* e;
   double theta = (e = getenv("MCD_LAP_THETA")) ? atof(e) : 4.0;
   if (!(theta > 1.0)) theta = 4.0;
@@ -1409,8 +1414,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
 
   lap_ctrl_init_kernel<<<1, 1, 0, h->stream>>>(s.ctrl, d_counters, 0);
   MCD_LAUNCH_CHECK(h, "lap_ctrl_init_kernel");
-  if (square_scaling) {
-    lap_minmax_kernel<<<h->sm_count * 2, 1024, 0, h->stream>>>(W, s.n, s.m, ldw, s.ctrl);
+  if (square_scaling || check_finite) {
+    lap_minmax_kernel<<<h->sm_count * 2, 1024, 0, h->stream>>>(W, s.n, s.m, ldw, s.ctrl, h->d_flags);
     MCD_LAUNCH_CHECK(h, "lap_minmax_kernel");
   }
   int per_sm = 0;

@@ -87,5 +87,6 @@ struct mcd_lap_counters {  // device-resident, one per solve
 };
 size_t mcd_lap_workspace_bytes(int64_t n, int64_t m);
 // Solve one rectangular max-assignment (n <= m).  `work` is mcd_lap_workspace_bytes(n, m) of device memory.
+// check_finite: also scan W for NaN/Inf (raises the context's non-finite flag; the solver kernels then no-op)
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
-                   double* objective, void* work, mcd_lap_counters* d_counters);
+                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite);

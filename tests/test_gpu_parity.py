@@ -286,3 +286,18 @@ def test_determinism(handle):
     a1, s1, o1, _ = handle.cell2cell(inst.rna, inst.dna, M, N, G)
     a2, s2, o2, _ = handle.cell2cell(inst.rna, inst.dna, M, N, G)
     assert (a1 == a2).all() and (s1 == s2).all() and (o1 == o2).all()
+
+
+def test_nonfinite_cost_matrix_is_reported(handle):
+    """mcd_lap_max / mcd_lap_steps on a user matrix with NaN must report MCD_ERR_NONFINITE, not crash."""
+    torch = _torch()
+    w = np.random.default_rng(1).random((40, 60))
+    w[3, 7] = np.nan
+    d_w = _dev(w)
+    d_col = torch.zeros(40, dtype=torch.int32, device="cuda")
+    st = handle.lib.mcd_lap_max(handle.h, d_w.data_ptr(), 40, 60, 60, d_col.data_ptr(), None)
+    assert st == -4
+    # and the handle is still usable afterwards
+    w[3, 7] = 0.5
+    col, obj = _lap_gpu(handle, w)
+    assert len(np.unique(col)) == 40
