@@ -15,9 +15,12 @@
 // FP64 registers (exact summation of the chunk partials).  That holds the error at the 1e-7 level
 // (north-star gate 1e-6) independent of K.
 //
-// Structure (one CTA per SM, persistent over 128 x 128 output tiles):
-//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the four slice tiles
-//               A_hi/A_lo, B_hi/B_lo [128 x 64] per k-block into a 3-stage ring (64 KB/stage)
+// Structure (one CTA per SM, persistent over 128 x 128 output tiles; CTAs run as CLUSTER PAIRS that work on
+// two horizontally adjacent tiles, i.e. share the RNA operand):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) into a 3-stage ring (64 KB/stage).  Each
+//               CTA fetches its own B_hi/B_lo tiles [128 x 64] but only HALF (64 rows) of A_hi/A_lo, with
+//               .multicast::cluster to both CTAs of the pair: L2->SM traffic per k-block drops from 64 to
+//               48 KB per CTA, which is what bounds this kernel (1 KB of operand per 128x128x3 MMA-k).
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
 //               12 per k-block; tcgen05.commit frees the smem stage / publishes the chunk accumulator
 //   warps 2-9   continuous epilogue: tcgen05.ld 32 lanes x 32 columns, FP64 accumulation of the chunk,
@@ -101,6 +104,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// commit that arrives on the barrier at the same smem offset in every CTA of `mask` (both CTAs of the pair)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // .aligned: the whole warp must be converged here
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -141,12 +162,16 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_np = (p.tiles_n + 1) >> 1;  // pair-columns; the odd one out is a phantom tile (all columns masked)
+  const int num_tiles = p.tiles_m * tiles_np;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 2);  // both CTAs of the pair must have consumed the stage (A is multicast)
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
@@ -165,6 +190,7 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -174,15 +200,17 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const uint32_t a_half = cta_rank * (A_SLICE_BYTES / 2);  // this CTA fetches rows [64*rank, 64*rank+64) of A
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tm = tile / tiles_np, tn = 2 * (tile % tiles_np) + (int)cta_rank;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          mbar_expect_tx(fb, STAGE_BYTES);  // 2 x 2 multicast A halves (own + peer's) + own B tiles
           const uint32_t st = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(st, &map_a_hi, fb, kb * BK, tm * BM);
-          tma_load_2d(st + A_SLICE_BYTES, &map_a_lo, fb, kb * BK, tm * BM);
+          tma_load_2d_mc(st + a_half, &map_a_hi, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2), (uint16_t)3);
+          tma_load_2d_mc(st + A_SLICE_BYTES + a_half, &map_a_lo, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2),
+                         (uint16_t)3);
           tma_load_2d(st + 2 * A_SLICE_BYTES, &map_b_hi, fb, kb * BK, tn * BN);
           tma_load_2d(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES, &map_b_lo, fb, kb * BK, tn * BN);
           if (++stage == STAGES) {
@@ -198,7 +226,7 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;  // chunk counter across tiles -> accumulator ring slot and parity
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         for (int kb0 = 0; kb0 < p.num_kb; kb0 += CHUNK_KB, ++g) {
           const uint32_t acc = g % NUM_ACC;
           const uint32_t acc_phase = (g / NUM_ACC) & 1;
@@ -221,7 +249,7 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
               umma_f16(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
               umma_f16(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
             }
-            umma_commit(empty_bar + 8 * stage);  // smem stage free once these MMAs retire
+            umma_commit_mc(empty_bar + 8 * stage, (uint16_t)3);  // stage free (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -236,8 +264,8 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;  // which 64-column half of the tile
     uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tm = tile / tiles_np, tn = 2 * (tile % tiles_np) + (int)cta_rank;
       double tot[EPI_COLS];
 #pragma unroll
       for (int q = 0; q < EPI_COLS; ++q) tot[q] = 0.0;
@@ -281,6 +309,7 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -325,7 +354,7 @@ int mcd_launch_corr_split(mcd_context* h, const uint16_t* A2, const uint16_t* A_
       (reinterpret_cast<uintptr_t>(A_lo) & 15) || (reinterpret_cast<uintptr_t>(B_lo) & 15) || (ldk16 % BK) != 0)
     return mcd_fail(h, MCD_ERR_INVALID, "corr_split: operands must be 16-byte aligned with ldk a multiple of 64");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (!make_map(&ma_hi, A2, M, ldk16, BM) || !make_map(&ma_lo, A_lo, M, ldk16, BM) ||
+  if (!make_map(&ma_hi, A2, M, ldk16, BM / 2) || !make_map(&ma_lo, A_lo, M, ldk16, BM / 2) ||
       !make_map(&mb_hi, B2, N, ldk16, BN) || !make_map(&mb_lo, B_lo, N, ldk16, BN))
     return mcd_fail(h, MCD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TcParams p;
@@ -341,9 +370,22 @@ int mcd_launch_corr_split(mcd_context* h, const uint16_t* A2, const uint16_t* A_
   p.Ct = Ct;
   p.ldct = ldct;
   MCD_CUDA(h, cudaFuncSetAttribute(corr_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  corr_split_kernel<<<grid, NUM_THREADS, SMEM_BYTES, h->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  MCD_LAUNCH_CHECK(h, "corr_split_kernel");
+  const int64_t pair_tiles = (int64_t)p.tiles_m * ((p.tiles_n + 1) / 2);
+  const int64_t max_pairs = h->sm_count / 2;
+  const int grid = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MCD_CUDA(h, cudaLaunchKernelEx(&cfg, corr_split_kernel, ma_hi, ma_lo, mb_hi, mb_lo, p));
+  h->launches++;
   return MCD_OK;
 }
