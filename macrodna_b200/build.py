@@ -40,6 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     common = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+    common += os.environ.get("MCD_NVCC_FLAGS", "").split()
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

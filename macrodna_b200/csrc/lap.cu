@@ -387,7 +387,7 @@ __device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int 
 }
 
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
-                                                                  int tail_nu, int use_lists) {
+                                                                  int tail_nu, int use_lists, int list_min_nu) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || s.flags[0]) return;  // uniform: written only at the very end of earlier launches
   const int first_phase = phase_idx == 0;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     }
     const long long t0 = clock64();
     const int* un = s.un[cur];
-    if (use_lists) {
+    if (use_lists && nu >= list_min_nu) {
       // ---- bidding, stage 1: one warp per bidder from its candidate list; failures go to a global list
       for (int k = (blockIdx.x * LAP_WARPS + warp); k < nu; k += gridDim.x * LAP_WARPS) {
         const int i = ldm(&un[k]);
@@ -942,6 +942,17 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
       Top2 t{NEG_INF, NEG_INF, -1, -1};
       int j = ws + 2 * lane;
       if (s.vec) {
+        for (; j + 15 * 64 + 1 < we; j += 16 * 64) {  // 16 independent 128-bit loads in flight per lane
+          double2 wv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + j + u * 64));
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const double2 pv = *reinterpret_cast<const double2*>(sprice + (j + u * 64 - o0));
+            top2_push_seq(t, wv[u].x - pv.x, j + u * 64);
+            top2_push_seq(t, wv[u].y - pv.y, j + u * 64 + 1);
+          }
+        }
         for (; j + 7 * 64 + 1 < we; j += 8 * 64) {  // 8 independent 128-bit loads in flight per lane
           double2 wv[8];
 #pragma unroll
@@ -1426,15 +1437,20 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   int blocks = h->sm_count * (per_sm < want ? per_sm : want);
   if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
   // Mode selection.
-  //   candidate lists + single-CTA tail : n < m and rows short enough that one SM sweeps them cheaply
-  //                                       (m <= 16384) -- the list failures that remain are rare and cheap
-  //   row sweeps + cluster tail         : long rows (every sweep is spread over the grid / over 8-16 SMs of a
-  //                                       cluster), and n == m (eps-scaling inflates every price, so a list
-  //                                       would be rebuilt on almost every bid)
+  //   n < m, short rows (m <= 16384)  : candidate lists everywhere + single-CTA narrow kernel (one SM sweeps a
+  //                                     short row cheaply, and list failures are rare)
+  //   n < m, long rows                : candidate lists in the rounds with >= a grid-full of bidders, split row
+  //                                     sweeps below that, DSMEM cluster kernel for the narrow rounds
+  //   n == m                          : no lists (eps-scaling inflates every price, a list would be rebuilt on
+  //                                     almost every bid): split row sweeps + cluster kernel
   int list_max_m = (e = getenv("MCD_LAP_LIST_MAX_M")) ? atoi(e) : 16384;
-  int use_lists = (n < m && m <= list_max_m) ? 1 : 0;
+  int use_lists = (n < m) ? 1 : 0;
   if ((e = getenv("MCD_LAP_LISTS"))) use_lists = atoi(e) ? 1 : 0;
-  const bool list_tail = use_lists != 0;
+  const bool list_tail = use_lists != 0 && m <= list_max_m;
+  // long rows: lists only pay in the rounds with at least a grid-full of bidders (failed lists are then swept by
+  // whole CTAs in parallel); below that every row is split over the grid instead
+  int list_min_nu = list_tail ? 0 : (blocks > 2048 ? blocks : 2048);
+  if ((e = getenv("MCD_LAP_LIST_MIN_NU"))) list_min_nu = atoi(e);
   int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? CL_MAX_CS : 8);
   if (cs > CL_MAX_CS) cs = CL_MAX_CS;
   size_t tail_smem = 0;
@@ -1460,7 +1476,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
 
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
-    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists};
+    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                             h->stream));
     h->launches++;
