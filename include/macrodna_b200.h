@@ -158,6 +158,14 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
 int mcd_transpose_f64(mcd_handle h, const double* src, int64_t rows, int64_t cols, int64_t lds, double* dst,
                       int64_t ldd);
 
+/*
+ * Matched correlation of every RNA cell, corr[i, assign[i]], of the LAST mcd_cell2cell call on this handle
+ * (its correlation matrix is still resident).  This is the `corr_val` column of the leave-one-out variant
+ * (Resampling_stability_analyses/BE_data_analyses/run_loo_experiment.py:194) and the operand of the median
+ * variant (random_assignment_test_median.py:196-199).  out [M] float64 in `out_space`.
+ */
+int mcd_last_match_values(mcd_handle h, double* out, int64_t M, int out_space);
+
 /* Number of steps ceil(M/N) (macrodna.py:118-123). */
 int64_t mcd_num_steps(int64_t M, int64_t N);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "mcd_corr_fp64": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_corr_split": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_transpose_f64": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I64]),
+    "mcd_last_match_values": (_I, [_VP, _VP, _I64, _I]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
     "mcd_cell2cell": (
@@ -182,6 +183,12 @@ class Handle:
         )
         self.check(st)
         return assign, step, step_obj, stats
+
+    def last_match_values(self, M):
+        """corr[i, assign[i]] of the last cell2cell call (matrix still resident on the device)."""
+        out = np.empty(M, dtype=np.float64)
+        self.check(self.lib.mcd_last_match_values(self.h, _ptr(out), M, MEM_HOST))
+        return out
 
     def lap_steps(self, C_ptr, ldc, Ct_ptr, ldct, M, N, out_space=MEM_HOST, assign=None, step=None, step_obj=None):
         nsteps = self.lib.mcd_num_steps(M, N)

@@ -38,11 +38,18 @@ class MaCroDNA:
     * ``precision``: ``"fp64"`` (parity mode, FP64 tensor pipe) or ``"split"`` (tcgen05 fp16 hi/lo split precision);
     * ``clone_column``: ``"predict_clone"`` (README.md:201, CRC_data_analysis/macrodna.py:195) or
       ``"predict"`` (src/MaCroDNA/macrodna.py:198);
-    * ``verbose``: print the reference's progress lines (``:95-98,120,124,147``).
+    * ``verbose``: print the reference's progress lines (``:95-98,120,124,147``);
+    * ``variant``: return signature of ``cell2cell_assignment`` -- the reference repo carries nine copies of the
+      class with drifting signatures (SURVEY.md section 2.2): ``"src"`` ``(res, tagged)``;
+      ``"objective"`` ``(res, tagged, sum(objVal))`` (random_assignment_test.py:196);
+      ``"median"`` ``(res, tagged, sum, median matched corr)`` (random_assignment_test_median.py:196-199);
+      ``"loo"`` ``(res, tagged[predicted_dna_cell, step, corr_val] indexed by rna_cell, sum, n_iters)``
+      (run_loo_experiment.py:194-199); ``"resampling"`` tagged frame only with columns
+      ``predicted_dna_cell, rna_cell, step`` and no index (clonal_proportions_resampling.py:166-169).
     """
 
     def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="fp64",
-                 clone_column="predict_clone", verbose=False):
+                 clone_column="predict_clone", verbose=False, variant="src"):
         self.rna_df = rna_df
         self.dna_df = dna_df
         self.dna_label = dna_label
@@ -50,6 +57,11 @@ class MaCroDNA:
         self.precision = precision
         self.clone_column = clone_column
         self.verbose = verbose
+        if variant not in ("src", "objective", "median", "loo", "resampling"):
+            raise ValueError("unknown variant %r" % (variant,))
+        self.variant = variant
+        self.keep_corr_val = variant in ("median", "loo")
+        self.last_corr_val = None   # matched correlation per RNA cell (variants "median" / "loo")
         self.last_stats = None      # dict of CUDA-event timings / solver counters of the last call
         self.last_objective = None  # per-step objective (the `m.objVal` of each reference `ilp` call)
         self.last_assign = None     # int32 DNA column per RNA cell
@@ -110,6 +122,7 @@ class MaCroDNA:
             raise ValueError("unassigned RNA cell")  # list.index(1), macrodna.py:160
         self.last_assign, self.last_step, self.last_objective = assign, step, objs
         self.last_stats = stats.as_dict()
+        self.last_corr_val = h.last_match_values(M) if self.keep_corr_val else None
         if self.verbose:
             for o in objs:
                 print("Obj: %g" % o)
@@ -126,13 +139,27 @@ class MaCroDNA:
         tmp_result = tmp_result.set_index("cell")  # macrodna.py:164-165
         tmp_result_tagged = pd.DataFrame(list(zip(pred, rna_cells, step.tolist())),
                                          columns=["predict_cell", "cell", "step"])
+        if self.variant == "resampling":
+            return pd.DataFrame(list(zip(pred, rna_cells, step.tolist())),
+                                columns=["predicted_dna_cell", "rna_cell", "step"])
+        if self.variant == "loo":
+            tagged = pd.DataFrame(list(zip(pred, rna_cells, step.tolist(), self.last_corr_val.tolist())),
+                                  columns=["predicted_dna_cell", "rna_cell", "step", "corr_val"]).set_index("rna_cell")
+            return tmp_result, tagged, float(np.sum(self.last_objective)), int(len(self.last_objective))
         tmp_result_tagged = tmp_result_tagged.set_index("cell")  # macrodna.py:182-184
+        if self.variant == "objective":
+            return tmp_result, tmp_result_tagged, float(np.sum(self.last_objective))
+        if self.variant == "median":
+            return (tmp_result, tmp_result_tagged, float(np.sum(self.last_objective)),
+                    float(np.median(self.last_corr_val)))
         return tmp_result, tmp_result_tagged
 
     def cell2clone_assignment(self):
         """macrodna.py:188-199: cell2cell + ``dna_label.set_index("cell").loc[predict_cell]["clone"]``."""
         if self.dna_label is None:
             raise ValueError("dna_label is required for cell2clone_assignment")
+        if self.variant != "src":
+            raise ValueError("cell2clone_assignment uses the 'src' return signature")
         rna_result, _ = self.cell2cell_assignment()
         dna_label = self.dna_label.set_index("cell")
         rna_result[self.clone_column] = dna_label.loc[rna_result["predict_cell"]]["clone"].tolist()

@@ -288,6 +288,15 @@ __global__ void transpose_f64_kernel(const double* __restrict__ src, int64_t row
   }
 }
 
+__global__ void gather_match_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ assign, int64_t M,
+                                    double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) {
+    const int j = assign[i];
+    out[i] = j >= 0 ? C[i * ldc + j] : 0.0;
+  }
+}
+
 cudaEvent_t get_event(mcd_context* h, size_t idx) {
   while (h->ev.size() <= idx) {
     cudaEvent_t e;
@@ -431,12 +440,35 @@ int mcd_transpose_f64(mcd_handle h, const double* src, int64_t rows, int64_t col
   return MCD_OK;
 }
 
+int mcd_last_match_values(mcd_handle h, double* out, int64_t M, int out_space) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!out || M < 1 || M != h->last_M || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_last_match_values: no matching mcd_cell2cell result is resident");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  const double* C = static_cast<const double*>(h->ws[WS_C].ptr);
+  double* tmp = out;
+  void* scratch = nullptr;
+  if (out_space != MCD_MEM_DEVICE) {
+    int st = mcd_ws(h, WS_W, (size_t)M * 8, &scratch);  // the step-loop block buffer is free between calls
+    if (st) return st;
+    tmp = static_cast<double*>(scratch);
+  }
+  gather_match_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(C, h->last_ldc, h->last_assign, M, tmp);
+  MCD_LAUNCH_CHECK(h, "gather_match_kernel");
+  if (out_space != MCD_MEM_DEVICE)
+    MCD_CUDA(h, cudaMemcpyAsync(out, tmp, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MCD_OK;
+}
+
 int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M, int64_t N,
                   int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats) {
   if (!h) return MCD_ERR_INVALID;
   if (!C || !Ct || !assign || !step || M < 1 || N < 1 || ldc < N || ldct < M || M > 0x3fffffff || N > 0x3fffffff)
     return mcd_fail(h, MCD_ERR_INVALID, "mcd_lap_steps arguments");
   MCD_CUDA(h, cudaSetDevice(h->device));
+  h->last_M = 0;  // the resident cell2cell result (if any) is about to be overwritten
+  h->last_assign = nullptr;
   const int64_t nsteps = mcd_num_steps(M, N);
   void* misc = nullptr;
   const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
@@ -674,8 +706,14 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
   }
+  h->last_M = 0;
+  h->last_assign = nullptr;
   if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the expression / copy-number matrix");
   if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  h->last_M = M;
+  h->last_N = N;
+  h->last_ldc = ldc;
+  h->last_assign = d_assign;
   return MCD_OK;
 }
 

@@ -28,6 +28,9 @@ struct mcd_context {
   size_t h_stage_bytes = 0;
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev;
+  // shape of the last mcd_cell2cell call whose correlation matrix / assignment are still resident
+  int64_t last_M = 0, last_N = 0, last_ldc = 0;
+  const int* last_assign = nullptr;
 };
 
 enum {
