@@ -43,6 +43,26 @@ UNIT = "s"
 FP64_NOMINAL_TFLOPS = 40.0  # B200 datasheet FP64 (tensor) -- MEASURED_PEAKS.json carries no FP64 figure
 
 
+def load_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of `scripts/profile_pass.py C5` (profiles/r01_C5_final_ncu_summary.json).  Valid for the C5 workload."""
+    p = os.path.join(ROOT, "profiles", "r01_C5_final_ncu_summary.json")
+    out = {}
+    if not os.path.exists(p):
+        return out
+    def gb(x):
+        try:
+            v, u = x.split()
+            return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+        except Exception:
+            return None
+    for k in json.load(open(p)).get("full_capture", []):
+        r, w = gb(k.get("dram_read", "")), gb(k.get("dram_write", ""))
+        if r is not None and w is not None and r == r and w == w:
+            out.setdefault(k["kernel"].split("<")[0], []).append(r + w)
+    return out
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -342,10 +362,22 @@ def main():
                     "scanned_gbs": st["lap_bytes"] / t_lap / 1e9, "rounds": st["lap_rounds"], "bids": st["lap_bids"],
                     "aug_rows": st["lap_aug_rows"], "peak_source": peaks["source"]},
         }
+        if args.workload == "C5":
+            tr = load_traffic()
+            if "standardize_rows" in tr:  # RNA operand launch (the larger of the two)
+                rooflines["standardize"]["traffic"] = max(tr["standardize_rows"])
+            if "corr_fp64_kernel" in tr and args.precision == "fp64":
+                rooflines["corr"]["traffic"] = tr["corr_fp64_kernel"][0]
+            if "lap_auction_kernel" in tr:
+                rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
+                rooflines["lap"]["traffic_note"] = ("one wide-round launch (step 2); ncu returns no DRAM counters for "
+                                                    "the cluster kernel of the narrow rounds")
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_rows", "corr": "corr_fp64_kernel" if args.precision == "fp64"
-                          else "corr_split_kernel", "lap": "lap_auction_kernel"}[dominant]
+                          else "corr_split_kernel",
+                          "lap": "lap_auction_kernel + lap_tail_cluster_kernel (assignment solver, all steps)"}[dominant]
+        roof["algorithmic_bytes"] = {"standardize": std_bytes, "corr": None, "lap": lap_bytes_alg}[dominant]
         line = {
             "metric": METRIC, "value": ms_dev * 1e-3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
