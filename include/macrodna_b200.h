@@ -159,6 +159,17 @@ int mcd_transpose_f64(mcd_handle h, const double* src, int64_t rows, int64_t col
                       int64_t ldd);
 
 /*
+ * Same as mcd_cell2cell, with the gene intersection applied on the device: the host passes the frames' value
+ * blocks as they are (rna [M, ld_rna], dna [N, ld_dna], any gene order, extra genes allowed) plus, per operand,
+ * the column index of each of the G shared genes (int32 [G], HOST; NULL = identity).  This is the reference's
+ * `.loc[genes, :]` re-indexing (macrodna.py:90-91) without the host copy of the matrices.
+ */
+int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const int32_t* rna_gene_idx,
+                         const double* dna, int64_t ld_dna, const int32_t* dna_gene_idx, int64_t M, int64_t N,
+                         int64_t G, int in_space, int precision, int32_t* assign, int32_t* step, double* step_obj,
+                         double* corr_out, int out_space, mcd_stats* stats);
+
+/*
  * Matched correlation of every RNA cell, corr[i, assign[i]], of the LAST mcd_cell2cell call on this handle
  * (its correlation matrix is still resident).  This is the `corr_val` column of the leave-one-out variant
  * (Resampling_stability_analyses/BE_data_analyses/run_loo_experiment.py:194) and the operand of the median

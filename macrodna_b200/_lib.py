@@ -80,6 +80,10 @@ SIGNATURES = {
     "mcd_last_match_values": (_I, [_VP, _VP, _I64, _I]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
+    "mcd_cell2cell_gather": (
+        _I,
+        [_VP, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)],
+    ),
     "mcd_cell2cell": (
         _I,
         [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _I, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)],
@@ -167,8 +171,11 @@ class Handle:
 
     # ---- whole path, host or device buffers -------------------------------------------------
     def cell2cell(self, rna, dna, M, N, G, ld_rna=None, ld_dna=None, in_space=MEM_HOST, precision="fp64",
-                  assign=None, step=None, step_obj=None, corr_out=None, out_space=MEM_HOST):
-        """``rna``/``dna``: numpy arrays (host) or integer device pointers; cells x genes float64."""
+                  assign=None, step=None, step_obj=None, corr_out=None, out_space=MEM_HOST, rna_gene_idx=None,
+                  dna_gene_idx=None):
+        """``rna``/``dna``: numpy arrays (host) or integer device pointers; cells x genes float64.
+        ``rna_gene_idx`` / ``dna_gene_idx``: optional int32 arrays [G] -- column of each shared gene in the
+        operand's block (the gene intersection is then gathered on the device)."""
         nsteps = self.lib.mcd_num_steps(M, N)
         if assign is None:
             assign = np.empty(M, dtype=np.int32)
@@ -177,9 +184,14 @@ class Handle:
         if step_obj is None:
             step_obj = np.empty(nsteps, dtype=np.float64)
         stats = McdStats()
-        st = self.lib.mcd_cell2cell(
-            self.h, _ptr(rna), ld_rna or G, _ptr(dna), ld_dna or G, M, N, G, in_space, PREC[precision],
-            _ptr(assign), _ptr(step), _ptr(step_obj), _ptr(corr_out), out_space, C.byref(stats),
+        if rna_gene_idx is not None:
+            rna_gene_idx = np.ascontiguousarray(rna_gene_idx, dtype=np.int32)
+        if dna_gene_idx is not None:
+            dna_gene_idx = np.ascontiguousarray(dna_gene_idx, dtype=np.int32)
+        st = self.lib.mcd_cell2cell_gather(
+            self.h, _ptr(rna), ld_rna or G, _ptr(rna_gene_idx), _ptr(dna), ld_dna or G, _ptr(dna_gene_idx), M, N, G,
+            in_space, PREC[precision], _ptr(assign), _ptr(step), _ptr(step_obj), _ptr(corr_out), out_space,
+            C.byref(stats),
         )
         self.check(st)
         return assign, step, step_obj, stats

@@ -50,6 +50,7 @@ class MaCroDNA:
 
     def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="fp64",
                  clone_column="predict_clone", verbose=False, variant="src"):
+        self._genes = None  # shared genes of the last run: the frames below are filtered lazily (see rna_df)
         self.rna_df = rna_df
         self.dna_df = dna_df
         self.dna_label = dna_label
@@ -67,22 +68,55 @@ class MaCroDNA:
         self.last_assign = None     # int32 DNA column per RNA cell
         self.last_step = None       # int32 1-based step per RNA cell
 
+    # -- the frames.  The reference overwrites self.rna_df / self.dna_df with the gene-filtered frames
+    #    (macrodna.py:90-91).  Here the filtering of the DATA happens on the device (index gather in K1), so the
+    #    host frames are only re-indexed if somebody actually looks at them after a run.
+    @property
+    def rna_df(self):
+        if self._genes is not None and self._rna_df is not None and not self._rna_filtered:
+            self._rna_df = self._rna_df.loc[self._genes, :]
+            self._rna_filtered = True
+        return self._rna_df
+
+    @rna_df.setter
+    def rna_df(self, df):
+        self._rna_df = df
+        self._rna_filtered = False
+        self._genes = None
+
+    @property
+    def dna_df(self):
+        if self._genes is not None and self._dna_df is not None and not self._dna_filtered:
+            self._dna_df = self._dna_df.loc[self._genes, :]
+            self._dna_filtered = True
+        return self._dna_df
+
+    @dna_df.setter
+    def dna_df(self, df):
+        self._dna_df = df
+        self._dna_filtered = False
+        self._genes = None
+
     # -- host bookkeeping -------------------------------------------------------------------------
     def _shared_genes(self):
-        """macrodna.py:89 -- set intersection; canonical order = DNA-frame order."""
-        rna_index = self.rna_df.index
-        dna_index = self.dna_df.index
+        """macrodna.py:89 -- set intersection; canonical order = DNA-frame order.
+        Returns (genes, column of each gene in the DNA block, column of each gene in the RNA block)."""
+        rna_index = self._rna_df.index
+        dna_index = self._dna_df.index
         if not dna_index.is_unique or not rna_index.is_unique:
             raise ValueError("duplicate gene labels in the expression / copy-number index")
-        keep = dna_index.isin(rna_index)
-        genes = dna_index[keep]
-        if len(genes) == 0:
+        pos_in_rna = rna_index.get_indexer(dna_index)
+        keep = pos_in_rna >= 0
+        if not keep.any():
             raise ValueError("rna_df and dna_df share no genes")
-        return genes
+        dna_pos = np.flatnonzero(keep).astype(np.int32)
+        rna_pos = pos_in_rna[keep].astype(np.int32)
+        return dna_index[keep], dna_pos, rna_pos
 
     @staticmethod
     def _cells_by_genes(df):
-        """macrodna.py:93-94 -- ``df.T.to_numpy()`` as C-contiguous float64 (cells x genes)."""
+        """macrodna.py:93-94 -- ``df.T.to_numpy()`` as C-contiguous float64 (cells x all genes of the frame).
+        For a single-dtype float64 frame this is a zero-copy view of the frame's block."""
         try:
             a = df.to_numpy(dtype=np.float64).T
         except (TypeError, ValueError) as e:
@@ -90,24 +124,24 @@ class MaCroDNA:
         return np.ascontiguousarray(a)
 
     def _run(self):
-        if self.rna_df is None or self.dna_df is None:
+        if self._rna_df is None or self._dna_df is None:
             raise ValueError("rna_df and dna_df are required")
-        dna_cells = list(self.dna_df.columns)  # macrodna.py:87
-        rna_cells = list(self.rna_df.columns)  # macrodna.py:88
+        dna_cells = list(self._dna_df.columns)  # macrodna.py:87
+        rna_cells = list(self._rna_df.columns)  # macrodna.py:88
         if len(set(rna_cells)) != len(rna_cells):
             # the reference dies later with "1 is not in list" (macrodna.py:159-160)
             raise ValueError("duplicate RNA cell ids")
         if len(rna_cells) == 0 or len(dna_cells) == 0:
             raise ValueError("empty input frame")
-        genes = self._shared_genes()
-        if not (len(genes) == len(self.dna_df.index) and genes.equals(self.dna_df.index)):
-            self.dna_df = self.dna_df.loc[genes, :]  # macrodna.py:90 (observable side effect)
-        if not (len(genes) == len(self.rna_df.index) and genes.equals(self.rna_df.index)):
-            self.rna_df = self.rna_df.loc[genes, :]  # macrodna.py:91
-        dna_np = self._cells_by_genes(self.dna_df)
-        rna_np = self._cells_by_genes(self.rna_df)
-        M, G = rna_np.shape
-        N = dna_np.shape[0]
+        genes, dna_pos, rna_pos = self._shared_genes()
+        dna_np = self._cells_by_genes(self._dna_df)  # [N, all DNA genes]
+        rna_np = self._cells_by_genes(self._rna_df)  # [M, all RNA genes]
+        M, N, G = rna_np.shape[0], dna_np.shape[0], len(genes)
+        # identity gathers are dropped (same genes, same order: the common preprocessed case)
+        if G == dna_np.shape[1] and (dna_pos == np.arange(G, dtype=np.int32)).all():
+            dna_pos = None
+        if G == rna_np.shape[1] and (rna_pos == np.arange(G, dtype=np.int32)).all():
+            rna_pos = None
         if self.verbose:
             print("number of cells in dna data %s" % N)
             print("number of cells in rna data %s" % M)
@@ -117,7 +151,11 @@ class MaCroDNA:
             print(q, r)
             print("MaCroDNA will be run for %s steps" % (q + (1 if r else 0)))
         h = get_handle(self.device)
-        assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, precision=self.precision)
+        assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, ld_rna=rna_np.shape[1], ld_dna=dna_np.shape[1],
+                                                precision=self.precision, rna_gene_idx=rna_pos, dna_gene_idx=dna_pos)
+        # macrodna.py:90-91: from now on the frames are the gene-filtered ones (materialised on first access)
+        if not self._rna_filtered or not self._dna_filtered or self._genes is None:
+            self._genes = genes
         if (assign < 0).any():
             raise ValueError("unassigned RNA cell")  # list.index(1), macrodna.py:160
         self.last_assign, self.last_step, self.last_objective = assign, step, objs

@@ -532,10 +532,23 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
 int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double* dna, int64_t ld_dna, int64_t M,
                   int64_t N, int64_t G, int in_space, int precision, int32_t* assign, int32_t* step, double* step_obj,
                   double* corr_out, int out_space, mcd_stats* stats) {
+  return mcd_cell2cell_gather(h, rna, ld_rna, nullptr, dna, ld_dna, nullptr, M, N, G, in_space, precision, assign, step,
+                              step_obj, corr_out, out_space, stats);
+}
+
+int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const int32_t* rna_gene_idx,
+                         const double* dna, int64_t ld_dna, const int32_t* dna_gene_idx, int64_t M, int64_t N,
+                         int64_t G, int in_space, int precision, int32_t* assign, int32_t* step, double* step_obj,
+                         double* corr_out, int out_space, mcd_stats* stats) {
   if (!h) return MCD_ERR_INVALID;
-  if (!rna || !dna || !assign || !step || M < 1 || N < 1 || G < 1 || ld_rna < G || ld_dna < G || M > 0x3fffffff ||
-      N > 0x3fffffff || G > 0x7fffffff)
+  if (!rna || !dna || !assign || !step || M < 1 || N < 1 || G < 1 || (!rna_gene_idx && ld_rna < G) ||
+      (!dna_gene_idx && ld_dna < G) || ld_rna < 1 || ld_dna < 1 || M > 0x3fffffff || N > 0x3fffffff || G > 0x7fffffff)
     return mcd_fail(h, MCD_ERR_INVALID, "mcd_cell2cell arguments");
+  for (int64_t g = 0; g < G; ++g) {
+    if ((rna_gene_idx && (rna_gene_idx[g] < 0 || rna_gene_idx[g] >= ld_rna)) ||
+        (dna_gene_idx && (dna_gene_idx[g] < 0 || dna_gene_idx[g] >= ld_dna)))
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_cell2cell_gather: gene index out of range");
+  }
   if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16)
     return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
   MCD_CUDA(h, cudaSetDevice(h->device));
@@ -575,25 +588,44 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
   const double* d_dna = dna;
   int64_t ldr = ld_rna, ldd = ld_dna;
   int nchunk = 1;
+  // gene gather indices (device copies); with a gather the staged rows keep all ld columns of the host block
+  const int* d_ridx = nullptr;
+  const int* d_didx = nullptr;
+  if (rna_gene_idx || dna_gene_idx) {
+    void* pg = nullptr;
+    if ((st = mcd_ws(h, WS_GIDX, (size_t)2 * G * 4, &pg))) return st;
+    int* gi = static_cast<int*>(pg);
+    if (rna_gene_idx) {
+      MCD_CUDA(h, cudaMemcpyAsync(gi, rna_gene_idx, (size_t)G * 4, cudaMemcpyHostToDevice, h->stream));
+      d_ridx = gi;
+    }
+    if (dna_gene_idx) {
+      MCD_CUDA(h, cudaMemcpyAsync(gi + G, dna_gene_idx, (size_t)G * 4, cudaMemcpyHostToDevice, h->stream));
+      d_didx = gi + G;
+    }
+  }
+  const int64_t wr = rna_gene_idx ? ld_rna : G;  // columns staged per RNA row
+  const int64_t wd = dna_gene_idx ? ld_dna : G;
   if (in_space == MCD_MEM_HOST) {
     void *pr = nullptr, *pd = nullptr;
-    if ((st = mcd_ws(h, WS_RNA_IN, (size_t)M * G * 8, &pr))) return st;
-    if ((st = mcd_ws(h, WS_DNA_IN, (size_t)N * G * 8, &pd))) return st;
-    MCD_CUDA(h, cudaMemcpy2DAsync(pd, (size_t)G * 8, dna, (size_t)ld_dna * 8, (size_t)G * 8, (size_t)N,
+    if ((st = mcd_ws(h, WS_RNA_IN, (size_t)M * wr * 8, &pr))) return st;
+    if ((st = mcd_ws(h, WS_DNA_IN, (size_t)N * wd * 8, &pd))) return st;
+    MCD_CUDA(h, cudaMemcpy2DAsync(pd, (size_t)wd * 8, dna, (size_t)ld_dna * 8, (size_t)wd * 8, (size_t)N,
                                   cudaMemcpyHostToDevice, h->stream));
     d_rna = static_cast<const double*>(pr);
     d_dna = static_cast<const double*>(pd);
-    ldr = ldd = G;
-    const double bytes = (double)M * G * 8;
+    ldr = wr;
+    ldd = wd;
+    const double bytes = (double)M * wr * 8;
     nchunk = (int)(bytes / (768.0 * 1024 * 1024)) + 1;
     if (nchunk > 16) nchunk = 16;
   }
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_H2D), h->stream));  // DNA operand resident
   // DNA operand: K1 once
   if (precision == MCD_PREC_FP64)
-    st = mcd_launch_standardize(h, d_dna, N, G, ldd, (double*)pb, ldk, nullptr, nullptr, 0, nB);
+    st = mcd_launch_standardize(h, d_dna, N, G, ldd, (double*)pb, ldk, nullptr, nullptr, 0, nB, d_didx);
   else
-    st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, b_hi, b_lo, ldk, nB);
+    st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, b_hi, b_lo, ldk, nB, d_didx);
   if (st) return st;
   int64_t rows_per = ((M + nchunk - 1) / nchunk + 127) / 128 * 128;
   if (rows_per < 128) rows_per = 128;
@@ -604,9 +636,9 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
     const int64_t mr = (M - r0 < rows_per) ? (M - r0) : rows_per;
     const int c = nchunk_used;
     if (in_space == MCD_MEM_HOST) {
-      double* dst = const_cast<double*>(d_rna) + r0 * G;
-      MCD_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)G * 8, rna + r0 * ld_rna, (size_t)ld_rna * 8, (size_t)G * 8, (size_t)mr,
-                                    cudaMemcpyHostToDevice, h->copy_stream));
+      double* dst = const_cast<double*>(d_rna) + r0 * wr;
+      MCD_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)wr * 8, rna + r0 * ld_rna, (size_t)ld_rna * 8, (size_t)wr * 8,
+                                    (size_t)mr, cudaMemcpyHostToDevice, h->copy_stream));
       MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c), h->copy_stream));
       MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(h, EV_CHUNK + 4 * c), 0));
     } else {
@@ -616,12 +648,13 @@ int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double*
     const double* xr = d_rna + r0 * ldr;
     if (precision == MCD_PREC_FP64) {
       double* ac = (double*)pa + r0 * ldk;
-      if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, ac, ldk, nullptr, nullptr, 0, nA + r0))) return st;
+      if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, ac, ldk, nullptr, nullptr, 0, nA + r0, d_ridx))) return st;
       MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
       if ((st = mcd_launch_corr_fp64(h, ac, mr, (double*)pb, N, ldk, nA + r0, nB, C + r0 * ldc, ldc, Ct + r0, ldct)))
         return st;
     } else {
-      if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, nullptr, 0, a_hi + r0 * ldk, a_lo + r0 * ldk, ldk, nA + r0)))
+      if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, nullptr, 0, a_hi + r0 * ldk, a_lo + r0 * ldk, ldk, nA + r0,
+                                       d_ridx)))
         return st;
       MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
       if ((st = mcd_launch_corr_split(h, a_hi + r0 * ldk, a_lo + r0 * ldk, mr, b_hi, b_lo, N, ldk, nA + r0, nB,

@@ -48,6 +48,7 @@ enum {
   WS_SLICES_A,
   WS_SLICES_B,
   WS_MISC,
+  WS_GIDX,  // gene gather indices (rna, dna)
 };
 
 int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);
@@ -70,7 +71,7 @@ int mcd_ws(mcd_context* h, int slot, size_t bytes, void** out);
 // slices_hi / slices_lo: the two fp16 slices (each [ncells, ldk16]); both NULL for the FP64 path
 int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
                            double* centred, int64_t ldk, uint16_t* slices_hi, uint16_t* slices_lo, int64_t ldk16,
-                           double* norms);
+                           double* norms, const int* gidx = nullptr);
 int mcd_launch_corr_fp64(mcd_context* h, const double* A, int64_t M, const double* B, int64_t N, int64_t ldk,
                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
 int mcd_launch_corr_split(mcd_context* h, const uint16_t* A_hi, const uint16_t* A_lo, int64_t M,

@@ -53,9 +53,13 @@ __device__ __forceinline__ void split_fp16x2(double y, uint16_t& s0, uint16_t& s
 }
 
 // T threads per row, NV double2 per thread (row capacity 2*T*NV elements), VEC = 128-bit loads legal.
+// gidx != nullptr: gene gather -- element g of the standardised row is X[row, gidx[g]] (the host only computes
+// the index arrays of the gene intersection, macrodna.py:89-91; the data never gets re-indexed on the host).
+// The row is then read with scattered 8-byte loads, but it is L1/L2 resident while its CTA works on it.
 template <int T, int NV, bool VEC>
 __global__ void __launch_bounds__((T > 512 ? T : 512), 1)
-standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ldx, double* __restrict__ Y,
+standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int G, int64_t ldx,
+                 double* __restrict__ Y,
                  int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
                  double* __restrict__ norms, int* __restrict__ flags) {
   constexpr int BLOCK = (T > 512 ? T : 512);
@@ -73,7 +77,10 @@ standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ld
     const int e = 2 * (t + k * T);
     double2 d = make_double2(0.0, 0.0);
     if (live) {
-      if (e + 1 < G) {
+      if (gidx != nullptr) {
+        if (e < G) d.x = __ldg(x + __ldg(gidx + e));
+        if (e + 1 < G) d.y = __ldg(x + __ldg(gidx + e + 1));
+      } else if (e + 1 < G) {
         if (VEC) {
           d = __ldcs(reinterpret_cast<const double2*>(x + e));
         } else {
@@ -147,19 +154,21 @@ standardize_rows(const double* __restrict__ X, int64_t ncells, int G, int64_t ld
 // Rows longer than the register-resident capacity: one 512-thread block per row, three sweeps
 // (the row stays L2-resident between sweeps; declared as a 3-read variant in DESIGN.md).
 __global__ void __launch_bounds__(512)
-standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, int64_t ldx, double* __restrict__ Y,
+standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int64_t G,
+                      int64_t ldx, double* __restrict__ Y,
                       int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
                       double* __restrict__ norms, int* __restrict__ flags) {
   __shared__ double red[16];
   const int64_t row = blockIdx.x;
   const double* x = X + row * ldx;
+  auto at = [&](int64_t e) { return gidx != nullptr ? x[gidx[e]] : x[e]; };
   double sum = 0.0;
-  for (int64_t e = threadIdx.x; e < G; e += 512) sum += x[e];
+  for (int64_t e = threadIdx.x; e < G; e += 512) sum += at(e);
   sum = group_sum<512, 512>(sum, red);
   const double mean = sum / (double)G;
   double ss = 0.0;
   for (int64_t e = threadIdx.x; e < G; e += 512) {
-    const double c = x[e] - mean;
+    const double c = at(e) - mean;
     ss += c * c;
   }
   ss = group_sum<512, 512>(ss, red);
@@ -171,14 +180,14 @@ standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, i
   const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
   if (Y != nullptr) {
     double* y = Y + row * ldk;
-    for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = e < G ? x[e] - mean : 0.0;
+    for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = e < G ? at(e) - mean : 0.0;
   }
   if (S != nullptr) {
     uint16_t* s0 = S + row * ldk16;
     uint16_t* s1 = S_lo + row * ldk16;
     for (int64_t e = threadIdx.x; e < ldk16; e += 512) {
       uint16_t a0 = 0, a1 = 0;
-      if (e < G) split_fp16x2((x[e] - mean) * inv, a0, a1);
+      if (e < G) split_fp16x2((at(e) - mean) * inv, a0, a1);
       s0[e] = a0;
       s1[e] = a1;
     }
@@ -186,17 +195,18 @@ standardize_rows_long(const double* __restrict__ X, int64_t ncells, int64_t G, i
 }
 
 template <int T, int NV>
-int launch_t(mcd_context* h, bool vec, const double* X, int64_t ncells, int G, int64_t ldx, double* Y, int64_t ldk,
+int launch_t(mcd_context* h, bool vec, const double* X, const int* gidx, int64_t ncells, int G, int64_t ldx, double* Y,
+             int64_t ldk,
              uint16_t* S, uint16_t* S_lo, int64_t ldk16, double* norms) {
   constexpr int BLOCK = (T > 512 ? T : 512);
   constexpr int ROWS = BLOCK / T;
   const int64_t grid = (ncells + ROWS - 1) / ROWS;
   if (vec)
-    standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, S_lo, ldk16,
-                                                                          norms, h->d_flags);
+    standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, gidx, ncells, G, ldx, Y, ldk, S, S_lo,
+                                                                          ldk16, norms, h->d_flags);
   else
-    standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, ncells, G, ldx, Y, ldk, S, S_lo, ldk16,
-                                                                           norms, h->d_flags);
+    standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, gidx, ncells, G, ldx, Y, ldk, S, S_lo,
+                                                                           ldk16, norms, h->d_flags);
   MCD_LAUNCH_CHECK(h, "standardize_rows");
   return MCD_OK;
 }
@@ -204,20 +214,21 @@ int launch_t(mcd_context* h, bool vec, const double* X, int64_t ncells, int G, i
 }  // namespace
 
 int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
-                           int64_t ldk, uint16_t* slices, uint16_t* slices_lo, int64_t ldk16, double* norms) {
+                           int64_t ldk, uint16_t* slices, uint16_t* slices_lo, int64_t ldk16, double* norms,
+                           const int* gidx) {
   if (ncells == 0) return MCD_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const int g = (int)G;
-  if (G <= 256) return launch_t<32, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 1024) return launch_t<128, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 4096) return launch_t<512, 4>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 8192) return launch_t<512, 8>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 12288) return launch_t<512, 12>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 16384) return launch_t<512, 16>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 20480) return launch_t<512, 20>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 24576) return launch_t<512, 24>(h, vec, X, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, ncells, G, ldx, centred, ldk, slices, slices_lo,
-                                                                ldk16, norms, h->d_flags);
+  if (G <= 256) return launch_t<32, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 1024) return launch_t<128, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 4096) return launch_t<512, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 8192) return launch_t<512, 8>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 12288) return launch_t<512, 12>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 16384) return launch_t<512, 16>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 20480) return launch_t<512, 20>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 24576) return launch_t<512, 24>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, gidx, ncells, G, ldx, centred, ldk, slices,
+                                                                slices_lo, ldk16, norms, h->d_flags);
   MCD_LAUNCH_CHECK(h, "standardize_rows_long");
   return MCD_OK;
 }

@@ -351,3 +351,24 @@ def test_replicate_sweep_matches_oracle(handle):
         assert (step == s_ref).all()
         # duplicated DNA cells are interchangeable: compare the ORIGINAL cell each RNA cell was given
         assert (cols[r][assign] == cols[r][a_ref]).all()
+
+
+def test_class_level_config3_with_device_gene_gather():
+    """Whole drop-in path at config 3: frames with shuffled RNA gene order and 3 % extra RNA genes, so the gene
+    intersection is applied by the device-side gather; result must equal the oracle's golden assignment."""
+    from macrodna_b200 import MaCroDNA, synth
+
+    g = np.load(os.path.join(GOLDEN, "synth_C3.npz"))
+    inst = synth.make_config_arrays("C3")
+    rna, dna, lab = synth.make_frames(inst)
+    assert list(rna.index) != list(dna.index) and len(rna.index) > len(dna.index)
+    m = MaCroDNA(rna, dna, lab)
+    res, tagged = m.cell2cell_assignment()
+    dna_cells = list(dna.columns)
+    assert res["predict_cell"].tolist() == [dna_cells[j] for j in g["assign"]]
+    assert tagged["step"].tolist() == g["step"].tolist()
+    assert np.allclose(m.last_objective, g["objs"], rtol=1e-9)
+    # the lazily materialised side effect of macrodna.py:90-91
+    assert list(m.rna_df.index) == list(dna.index) and m.rna_df.shape == (len(dna.index), rna.shape[1])
+    clone = MaCroDNA(rna, dna, lab).cell2clone_assignment()
+    assert (clone["predict_clone"].to_numpy() == inst.dna_clone[g["assign"]]).all()
