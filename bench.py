@@ -155,6 +155,12 @@ def cpu_baseline(M, N, G, clones, budget_s=20.0):
 
     cores = os.cpu_count() or 1
     full_pairs = float(M) * N
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the dgemm every host core back
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
 
     def run(scale, corr_rows=1.0):
         m, n = max(2, int(M * scale)), max(2, int(N * scale))
