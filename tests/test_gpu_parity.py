@@ -372,3 +372,41 @@ def test_class_level_config3_with_device_gene_gather():
     assert list(m.rna_df.index) == list(dna.index) and m.rna_df.shape == (len(dna.index), rna.shape[1])
     clone = MaCroDNA(rna, dna, lab).cell2clone_assignment()
     assert (clone["predict_clone"].to_numpy() == inst.dna_clone[g["assign"]]).all()
+
+
+@pytest.mark.parametrize("mn", [(700, 5), (300, 299), (50, 700), (2500, 1200)])
+def test_step_loop_shapes_many_steps_and_wide(handle, mn):
+    """140-step schedule (more steps than the per-step stats slots), near-square, M << N, and a mid-size case that
+    exercises the candidate-list kernels and the eps-scaled square-free last step."""
+    from oracle import restatement as R
+
+    M, N = mn
+    rng = np.random.default_rng(M + N)
+    base = rng.standard_normal((M, 8)) @ rng.standard_normal((8, N))  # low-rank structure: flat, contested costs
+    corrs = 0.15 * np.tanh(base / 3.0) + 0.01 * rng.standard_normal((M, N))
+    a_ref, s_ref, o_ref = R.step_loop(corrs)
+    d_c, d_ct = _dev(corrs), _dev(corrs.T)  # keep the tensors alive across the call
+    a, s, o, stats = handle.lap_steps(d_c.data_ptr(), N, d_ct.data_ptr(), M, M, N)
+    assert np.allclose(o, o_ref, rtol=1e-12, atol=1e-13)
+    assert (s == s_ref).all() and (a == a_ref).all()
+    assert stats.n_steps == R.n_steps(M, N)
+
+
+def test_standardize_split_long_rows(handle):
+    """G beyond the register-resident capacity (declared 3-sweep variant), split-precision output."""
+    torch = _torch()
+    from oracle import restatement as R
+
+    G, n = 30001, 9
+    x = np.log1p(np.random.default_rng(4).poisson(5.0, size=(n, G)).astype(np.float64))
+    lib, h = handle.lib, handle.h
+    ldk = lib.mcd_padded_k_split(G)
+    a2 = torch.empty((2, n, ldk), dtype=torch.int16, device="cuda")
+    na = torch.empty(n, dtype=torch.float64, device="cuda")
+    handle.check(lib.mcd_standardize_split(h, _dev(x).data_ptr(), n, G, G, a2.data_ptr(), na.data_ptr()))
+    handle.synchronize()
+    xc, nrm = R.standardise(x)
+    a = a2.cpu().numpy()
+    rec = (a[0].view(np.float16).astype(np.float64) + a[1].view(np.float16).astype(np.float64))[:, :G] / 256.0
+    assert np.abs(rec - xc / nrm[:, None]).max() < 2.0 ** -21
+    assert (a[:, :, G:] == 0).all()
