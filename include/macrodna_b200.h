@@ -40,7 +40,9 @@ typedef enum {
 /* Arithmetic of the correlation contraction (macrodna.py:103-107). */
 typedef enum {
   MCD_PREC_FP64 = 0,  /* FP64 tensor-core (DMMA) contraction of centred rows: parity mode   */
-  MCD_PREC_SPLIT_FP16 = 1 /* tcgen05 split precision: fp16 hi+lo slices, 3 products, FP32 in TMEM */
+  MCD_PREC_SPLIT_FP16 = 1, /* tcgen05 split precision: fp16 hi+lo slices, 3 products, FP32 in TMEM */
+  MCD_PREC_OZAKI_INT8 = 2  /* tcgen05 int8 digit slices (Ozaki scheme), exact int32 accumulation in TMEM,
+                              FP64 combination: FP64-class results from the integer tensor pipe          */
 } mcd_precision;
 
 /* Where a caller buffer lives. */
@@ -102,6 +104,13 @@ int mcd_standardize(mcd_handle h, const double* X, int64_t ncells, int64_t G, in
 int64_t mcd_padded_k_split(int64_t G);
 int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
                            uint16_t* slices, double* norms);
+/* Same pass, but emits the integer operand of MCD_PREC_OZAKI_INT8: every unit-norm centred row, scaled by a
+ * per-row power of two so that max|.| lies in [0.25, 0.5), as `nsl` balanced radix-128 digit slices:
+ *   digits [nsl, ncells, ldk8] int8, ldk8 = mcd_padded_k_split(G), zero padded;  scale [ncells] = 2^-e (the
+ *   factor that undoes the row scaling);  nsl in [2, 8] (mcd_ozaki_default_slices(): 6, env MCD_OZAKI_SLICES). */
+int mcd_ozaki_default_slices(void);
+int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
+                          int nsl, double* scale, double* norms);
 /* Synchronise and return MCD_ERR_NONFINITE if any standardise call since the last check saw NaN/Inf. */
 int mcd_check_finite(mcd_handle h);
 
@@ -119,6 +128,13 @@ int mcd_corr_fp64(mcd_handle h, const double* A, int64_t M, const double* B, int
 int mcd_corr_split(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* B3, int64_t N,
                     int64_t G, int64_t ldk16, const double* nA, const double* nB, double* C,
                     int64_t ldc, double* Ct, int64_t ldct);
+
+/* tcgen05 int8 variant on the digit slices of mcd_standardize_ozaki: all slice products with t + t' < nsl,
+ * exact int32 accumulation per significance group in TMEM (cta_group::2, 256 x 256 tiles), FP64 epilogue.
+ * MCD_ERR_UNSUPPORTED if nsl * 4096 * ldk8 >= 2^31 (the int32 accumulators could overflow). */
+int mcd_corr_ozaki(mcd_handle h, const int8_t* A8, int64_t M, const int8_t* B8, int64_t N, int64_t G, int64_t ldk8,
+                   int nsl, const double* sA, const double* sB, const double* nA, const double* nB, double* C,
+                   int64_t ldc, double* Ct, int64_t ldct);
 
 /*
  * K3 -- one rectangular assignment.  Replaces one `ilp` call (macrodna.py:27-84):

@@ -21,7 +21,7 @@ MCD_ERR_NONFINITE = -4
 MCD_ERR_UNSUPPORTED = -5
 MCD_ERR_NOT_CONVERGED = -6
 
-PREC = {"fp64": 0, "split": 1}
+PREC = {"fp64": 0, "split": 1, "ozaki": 2}
 MEM_HOST, MEM_DEVICE = 0, 1
 MAX_STEP_STATS = 64
 
@@ -73,6 +73,9 @@ SIGNATURES = {
     "mcd_num_steps": (_I64, [_I64, _I64]),
     "mcd_standardize": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_standardize_split": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_ozaki_default_slices": (_I, []),
+    "mcd_standardize_ozaki": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP, _VP]),
+    "mcd_corr_ozaki": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_check_finite": (_I, [_VP]),
     "mcd_corr_fp64": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_corr_split": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I64, _VP, _I64]),

@@ -1,5 +1,6 @@
 // C ABI of the hot path (include/macrodna_b200.h): context, workspace, step loop (K4), fused driver.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -137,6 +138,41 @@ int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t
   MCD_CUDA(h, cudaSetDevice(h->device));
   const int64_t ldk16 = mcd_padded_k_split(G);
   return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, slices, slices + ncells * ldk16, ldk16, norms);
+}
+
+int mcd_ozaki_default_slices(void) {
+  const char* e = getenv("MCD_OZAKI_SLICES");
+  int v = e ? atoi(e) : 6;
+  if (v < 2) v = 2;
+  if (v > MCD_OZAKI_MAX_SLICES) v = MCD_OZAKI_MAX_SLICES;
+  return v;
+}
+
+int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
+                          int nsl, double* scale, double* norms) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!X || !digits || !scale || !norms || ncells < 0 || G < 1 || ldx < G || G > 0x7fffffff || nsl < 2 ||
+      nsl > MCD_OZAKI_MAX_SLICES)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_standardize_ozaki arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  mcd_ozaki_out oz;
+  oz.digits = digits;
+  oz.ldk8 = mcd_padded_k_split(G);
+  oz.slice_stride = ncells * oz.ldk8;
+  oz.nsl = nsl;
+  oz.scale = scale;
+  return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, nullptr, nullptr, 0, norms, nullptr, &oz);
+}
+
+int mcd_corr_ozaki(mcd_handle h, const int8_t* A8, int64_t M, const int8_t* B8, int64_t N, int64_t G, int64_t ldk8,
+                   int nsl, const double* sA, const double* sB, const double* nA, const double* nB, double* C,
+                   int64_t ldc, double* Ct, int64_t ldct) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!A8 || !B8 || !sA || !sB || !nA || !nB || (!C && !Ct) || M < 0 || N < 0 || G < 1 || ldk8 < G ||
+      (ldk8 % 64) != 0 || (C && ldc < N) || (Ct && ldct < M))
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_ozaki arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  return mcd_launch_corr_ozaki(h, A8, M * ldk8, M, B8, N * ldk8, N, ldk8, nsl, sA, sB, nA, nB, C, ldc, Ct, ldct);
 }
 
 int mcd_check_finite(mcd_handle h) {
@@ -549,8 +585,12 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
         (dna_gene_idx && (dna_gene_idx[g] < 0 || dna_gene_idx[g] >= ld_dna)))
       return mcd_fail(h, MCD_ERR_INVALID, "mcd_cell2cell_gather: gene index out of range");
   }
-  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16)
+  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16 && precision != MCD_PREC_OZAKI_INT8)
     return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
+  const int nsl = mcd_ozaki_default_slices();
+  // exact int32 accumulation bounds the gene count of the integer path; longer rows use the FP64 pipe
+  if (precision == MCD_PREC_OZAKI_INT8 && (double)nsl * 4096.0 * (double)mcd_padded_k_split(G) >= 2147483648.0)
+    precision = MCD_PREC_FP64;
   MCD_CUDA(h, cudaSetDevice(h->device));
   const int64_t launches0 = h->launches;
   enum { EV_T0 = 0, EV_H2D, EV_STD, EV_CORR, EV_LAPEND, EV_D2H, EV_LAP = 8 };
@@ -570,9 +610,17 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   double* nB = static_cast<double*>(pnB);
   const int64_t ldk = precision == MCD_PREC_FP64 ? mcd_padded_k(G) : mcd_padded_k_split(G);
   void *pa = nullptr, *pb = nullptr;
+  double *sA = nullptr, *sB = nullptr;
   if (precision == MCD_PREC_FP64) {
     if ((st = mcd_ws(h, WS_RNA_C, (size_t)M * ldk * 8, &pa))) return st;
     if ((st = mcd_ws(h, WS_DNA_C, (size_t)N * ldk * 8, &pb))) return st;
+  } else if (precision == MCD_PREC_OZAKI_INT8) {
+    void* ps = nullptr;
+    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)nsl * M * ldk, &pa))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)nsl * N * ldk, &pb))) return st;
+    if ((st = mcd_ws(h, WS_SCALE, (size_t)(M + N) * 8, &ps))) return st;
+    sA = static_cast<double*>(ps);
+    sB = sA + M;
   } else {
     if ((st = mcd_ws(h, WS_SLICES_A, (size_t)2 * M * ldk * 2, &pa))) return st;
     if ((st = mcd_ws(h, WS_SLICES_B, (size_t)2 * N * ldk * 2, &pb))) return st;
@@ -622,8 +670,18 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   }
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_H2D), h->stream));  // DNA operand resident
   // DNA operand: K1 once
+  mcd_ozaki_out ozb, oza;
+  ozb.digits = static_cast<int8_t*>(pb);
+  ozb.ldk8 = ldk;
+  ozb.slice_stride = N * ldk;
+  ozb.nsl = nsl;
+  ozb.scale = sB;
+  oza = ozb;
+  oza.slice_stride = M * ldk;
   if (precision == MCD_PREC_FP64)
     st = mcd_launch_standardize(h, d_dna, N, G, ldd, (double*)pb, ldk, nullptr, nullptr, 0, nB, d_didx);
+  else if (precision == MCD_PREC_OZAKI_INT8)
+    st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, nullptr, nullptr, 0, nB, d_didx, &ozb);
   else
     st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, b_hi, b_lo, ldk, nB, d_didx);
   if (st) return st;
@@ -651,6 +709,15 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
       if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, ac, ldk, nullptr, nullptr, 0, nA + r0, d_ridx))) return st;
       MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
       if ((st = mcd_launch_corr_fp64(h, ac, mr, (double*)pb, N, ldk, nA + r0, nB, C + r0 * ldc, ldc, Ct + r0, ldct)))
+        return st;
+    } else if (precision == MCD_PREC_OZAKI_INT8) {
+      oza.digits = static_cast<int8_t*>(pa) + r0 * ldk;
+      oza.scale = sA + r0;
+      if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, nullptr, 0, nullptr, nullptr, 0, nA + r0, d_ridx, &oza)))
+        return st;
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c + 2), h->stream));
+      if ((st = mcd_launch_corr_ozaki(h, oza.digits, oza.slice_stride, mr, ozb.digits, ozb.slice_stride, N, ldk, nsl,
+                                      sA + r0, sB, nA + r0, nB, C + r0 * ldc, ldc, Ct + r0, ldct)))
         return st;
     } else {
       if ((st = mcd_launch_standardize(h, xr, mr, G, ldr, nullptr, 0, a_hi + r0 * ldk, a_lo + r0 * ldk, ldk, nA + r0,

@@ -22,7 +22,7 @@ struct mcd_context {
   int* d_flags = nullptr;  // [0] non-finite input seen, [1..] spare
   int64_t launches = 0;
   // grow-only device workspace slots (reused across calls)
-  mcd_buffer ws[16];
+  mcd_buffer ws[20];
   // pinned host staging
   void* h_stage[2] = {nullptr, nullptr};
   size_t h_stage_bytes = 0;
@@ -49,6 +49,7 @@ enum {
   WS_SLICES_B,
   WS_MISC,
   WS_GIDX,  // gene gather indices (rna, dna)
+  WS_SCALE, // Ozaki row scales (rna then dna)
 };
 
 int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);
@@ -67,11 +68,28 @@ int mcd_ws(mcd_context* h, int slot, size_t bytes, void** out);
     if (e__ != cudaSuccess) return mcd_fail((h), MCD_ERR_CUDA, name, e__); \
   } while (0)
 
+// int8 digit-slice operand of the Ozaki path (K1 output, K2c input):
+//   digits [nsl, ncells(+), ldk8] int8 -- slice t of row r starts at digits + t*slice_stride + r*ldk8
+//   scale  [ncells] double           -- 2^-e of the per-row power-of-two scaling
+#define MCD_OZAKI_MAX_SLICES 8
+struct mcd_ozaki_out {
+  int8_t* digits = nullptr;
+  int64_t ldk8 = 0;
+  int64_t slice_stride = 0;
+  int nsl = 0;
+  double* scale = nullptr;
+};
+
 // ---- kernel launchers (each returns an mcd_status) -------------------------------------------
 // slices_hi / slices_lo: the two fp16 slices (each [ncells, ldk16]); both NULL for the FP64 path
 int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx,
                            double* centred, int64_t ldk, uint16_t* slices_hi, uint16_t* slices_lo, int64_t ldk16,
-                           double* norms, const int* gidx = nullptr);
+                           double* norms, const int* gidx = nullptr, const mcd_ozaki_out* ozaki = nullptr);
+// K2c: C = sum over genes of the digit-slice products (exact int32 accumulation in TMEM), FP64 epilogue.
+// A: nsl slices of [M, ldk8] int8 (slice stride a_stride elements), B likewise; sA/sB the row scales.
+int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int64_t M, const int8_t* B,
+                          int64_t b_stride, int64_t N, int64_t ldk8, int nsl, const double* sA, const double* sB,
+                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
 int mcd_launch_corr_fp64(mcd_context* h, const double* A, int64_t M, const double* B, int64_t N, int64_t ldk,
                          const double* nA, const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
 int mcd_launch_corr_split(mcd_context* h, const uint16_t* A_hi, const uint16_t* A_lo, int64_t M,

@@ -40,6 +40,41 @@ __device__ __forceinline__ double group_sum(double v, double* red) {
   return s;
 }
 
+// Max over the T threads that own one row (same protocol as group_sum).
+template <int T, int BLOCK>
+__device__ __forceinline__ double group_max(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (T == 32) return v;
+  constexpr int WPG = T / 32;
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  const int g0 = (warp / WPG) * WPG;
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < WPG; ++w) s = fmax(s, red[g0 + w]);
+  return s;
+}
+
+// Integer-slice operand of the int8 tensor-core path (corr_ozaki.cu).  y (|y| < 0.5) is rounded to the
+// fixed-point integer q = rint(y * 2^(7*nsl-1)) and written as nsl balanced radix-128 digits d_t in [-64, 63],
+//   q = sum_t d_t * 128^(nsl-1-t)      (t = 0 is the most significant slice).
+// The products of two such digit vectors are exact in the tensor core's int32 accumulators.
+__device__ __forceinline__ void ozaki_digits(double y, int nsl, int d[MCD_OZAKI_MAX_SLICES]) {
+  long long q = __double2ll_rn(scalbn(y, 7 * nsl - 1));
+#pragma unroll
+  for (int t = MCD_OZAKI_MAX_SLICES - 1; t >= 0; --t) {
+    d[t] = 0;
+    if (t < nsl) {
+      const int r = (int)((q + 64) & 127) - 64;
+      d[t] = r;
+      q = (q - r) >> 7;
+    }
+  }
+}
+
 // Split-precision operand for the tcgen05 path: y (|y| <= 1, a unit-norm centred value) is scaled by
 // 2^8 and written as fp16 hi + fp16 lo (22 significant bits; the scale keeps `lo` out of the fp16
 // subnormal range for every |y| > 5e-4).  hi*hi + hi*lo + lo*hi reproduces the product to ~2^-22.
@@ -61,7 +96,7 @@ __global__ void __launch_bounds__((T > 512 ? T : 512), 1)
 standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int G, int64_t ldx,
                  double* __restrict__ Y,
                  int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
-                 double* __restrict__ norms, int* __restrict__ flags) {
+                 double* __restrict__ norms, int* __restrict__ flags, const mcd_ozaki_out oz) {
   constexpr int BLOCK = (T > 512 ? T : 512);
   constexpr int ROWS = BLOCK / T;
   __shared__ double red[BLOCK / 32];
@@ -108,10 +143,44 @@ standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int
   }
   ss = group_sum<T, BLOCK>(ss, red);
   const double nrm = sqrt(ss);
+  double amax = 0.0;
+  if (oz.digits != nullptr) {  // uniform over the block
+#pragma unroll
+    for (int k = 0; k < NV; ++k) amax = fmax(amax, fmax(fabs(v[k].x), fabs(v[k].y)));
+    amax = group_max<T, BLOCK>(amax, red);
+  }
   if (!live) return;
   if (t == 0) {
     norms[row] = nrm;
     if (!isfinite(sum) || !isfinite(ss)) atomicOr(flags, 1);
+  }
+  if (oz.digits != nullptr) {
+    // unit row u = c / nrm scaled by 2^e so that max|u| * 2^e lies in [0.25, 0.5)
+    const double inv = (nrm > 0.0 && isfinite(nrm)) ? 1.0 / nrm : 0.0;
+    const double umax = amax * inv;
+    int ex = 0;
+    if (umax > 0.0 && isfinite(umax)) (void)frexp(umax, &ex);  // umax = f * 2^ex, f in [0.5, 1)
+    const int e = -ex - 1;
+    if (t == 0) oz.scale[row] = scalbn(1.0, -e);
+    int8_t* o = oz.digits + row * oz.ldk8;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int g = 2 * (t + k * T);
+      if (g < G) {
+        int d0[MCD_OZAKI_MAX_SLICES], d1[MCD_OZAKI_MAX_SLICES];
+        ozaki_digits(scalbn(v[k].x * inv, e), oz.nsl, d0);
+        ozaki_digits((g + 1 < G) ? scalbn(v[k].y * inv, e) : 0.0, oz.nsl, d1);
+#pragma unroll
+        for (int sl = 0; sl < MCD_OZAKI_MAX_SLICES; ++sl)
+          if (sl < oz.nsl)  // g is even and ldk8 a multiple of 64: aligned 2-byte store
+            *reinterpret_cast<uint16_t*>(o + sl * oz.slice_stride + g) =
+                (uint16_t)((uint32_t)(d0[sl] & 0xff) | ((uint32_t)(d1[sl] & 0xff) << 8));
+      }
+    }
+    const int64_t g2 = (G + 1) & ~1;
+    for (int sl = 0; sl < oz.nsl; ++sl)
+      for (int64_t c = g2 + 2 * t; c < oz.ldk8; c += 2 * T)
+        *reinterpret_cast<uint16_t*>(o + sl * oz.slice_stride + c) = 0;
   }
 
   if (Y != nullptr) {
@@ -157,7 +226,7 @@ __global__ void __launch_bounds__(512)
 standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int64_t G,
                       int64_t ldx, double* __restrict__ Y,
                       int64_t ldk, uint16_t* __restrict__ S, uint16_t* __restrict__ S_lo, int64_t ldk16,
-                      double* __restrict__ norms, int* __restrict__ flags) {
+                      double* __restrict__ norms, int* __restrict__ flags, const mcd_ozaki_out oz) {
   __shared__ double red[16];
   const int64_t row = blockIdx.x;
   const double* x = X + row * ldx;
@@ -182,6 +251,25 @@ standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx
     double* y = Y + row * ldk;
     for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = e < G ? at(e) - mean : 0.0;
   }
+  if (oz.digits != nullptr) {
+    double amax = 0.0;
+    for (int64_t e = threadIdx.x; e < G; e += 512) amax = fmax(amax, fabs(at(e) - mean));
+    amax = group_max<512, 512>(amax, red);
+    const double inv1 = (nrm > 0.0 && isfinite(nrm)) ? 1.0 / nrm : 0.0;
+    const double umax = amax * inv1;
+    int ex = 0;
+    if (umax > 0.0 && isfinite(umax)) (void)frexp(umax, &ex);
+    const int sh = -ex - 1;
+    if (threadIdx.x == 0) oz.scale[row] = scalbn(1.0, -sh);
+    int8_t* o = oz.digits + row * oz.ldk8;
+    for (int64_t e = threadIdx.x; e < oz.ldk8; e += 512) {
+      int d[MCD_OZAKI_MAX_SLICES];
+      ozaki_digits(e < G ? scalbn((at(e) - mean) * inv1, sh) : 0.0, oz.nsl, d);
+#pragma unroll
+      for (int sl = 0; sl < MCD_OZAKI_MAX_SLICES; ++sl)
+        if (sl < oz.nsl) o[sl * oz.slice_stride + e] = (int8_t)d[sl];
+    }
+  }
   if (S != nullptr) {
     uint16_t* s0 = S + row * ldk16;
     uint16_t* s1 = S_lo + row * ldk16;
@@ -197,16 +285,16 @@ standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx
 template <int T, int NV>
 int launch_t(mcd_context* h, bool vec, const double* X, const int* gidx, int64_t ncells, int G, int64_t ldx, double* Y,
              int64_t ldk,
-             uint16_t* S, uint16_t* S_lo, int64_t ldk16, double* norms) {
+             uint16_t* S, uint16_t* S_lo, int64_t ldk16, double* norms, const mcd_ozaki_out& oz) {
   constexpr int BLOCK = (T > 512 ? T : 512);
   constexpr int ROWS = BLOCK / T;
   const int64_t grid = (ncells + ROWS - 1) / ROWS;
   if (vec)
     standardize_rows<T, NV, true><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, gidx, ncells, G, ldx, Y, ldk, S, S_lo,
-                                                                          ldk16, norms, h->d_flags);
+                                                                          ldk16, norms, h->d_flags, oz);
   else
     standardize_rows<T, NV, false><<<(unsigned)grid, BLOCK, 0, h->stream>>>(X, gidx, ncells, G, ldx, Y, ldk, S, S_lo,
-                                                                           ldk16, norms, h->d_flags);
+                                                                           ldk16, norms, h->d_flags, oz);
   MCD_LAUNCH_CHECK(h, "standardize_rows");
   return MCD_OK;
 }
@@ -215,20 +303,22 @@ int launch_t(mcd_context* h, bool vec, const double* X, const int* gidx, int64_t
 
 int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int64_t G, int64_t ldx, double* centred,
                            int64_t ldk, uint16_t* slices, uint16_t* slices_lo, int64_t ldk16, double* norms,
-                           const int* gidx) {
+                           const int* gidx, const mcd_ozaki_out* ozaki) {
   if (ncells == 0) return MCD_OK;
+  mcd_ozaki_out oz{};
+  if (ozaki != nullptr) oz = *ozaki;
   const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const int g = (int)G;
-  if (G <= 256) return launch_t<32, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 1024) return launch_t<128, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 4096) return launch_t<512, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 8192) return launch_t<512, 8>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 12288) return launch_t<512, 12>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 16384) return launch_t<512, 16>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 20480) return launch_t<512, 20>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
-  if (G <= 24576) return launch_t<512, 24>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms);
+  if (G <= 256) return launch_t<32, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 1024) return launch_t<128, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 4096) return launch_t<512, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 8192) return launch_t<512, 8>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 12288) return launch_t<512, 12>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 16384) return launch_t<512, 16>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 20480) return launch_t<512, 20>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
+  if (G <= 24576) return launch_t<512, 24>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
   standardize_rows_long<<<(unsigned)ncells, 512, 0, h->stream>>>(X, gidx, ncells, G, ldx, centred, ldk, slices,
-                                                                slices_lo, ldk16, norms, h->d_flags);
+                                                                slices_lo, ldk16, norms, h->d_flags, oz);
   MCD_LAUNCH_CHECK(h, "standardize_rows_long");
   return MCD_OK;
 }

@@ -1,0 +1,127 @@
+"""GPU tests of the int8 tcgen05 Ozaki-scheme correlation path (precision="ozaki").
+
+The digit-slice products are exact in the tensor core (int8 x int8 -> int32), so the only error is the
+fixed-point resolution of the slices: with the default 6 slices the correlations agree with the float64
+oracle to ~1e-12 absolute, with 8 slices to the oracle's own rounding level.  Gate here: 1e-10 (6 slices),
+far inside the north star's 1e-6, and the whole path must reproduce the FP64 oracle's assignments."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _corr_ozaki(handle, rna, dna, nsl, with_c=True, with_ct=True):
+    torch = _torch()
+    lib, h = handle.lib, handle.h
+    M, G = rna.shape
+    N = dna.shape[0]
+    ldk = lib.mcd_padded_k_split(G)
+    d_r = torch.from_numpy(rna).cuda()
+    d_d = torch.from_numpy(dna).cuda()
+    a8 = torch.full((nsl, M, ldk), 55, dtype=torch.int8, device="cuda")
+    b8 = torch.full((nsl, N, ldk), 55, dtype=torch.int8, device="cuda")
+    na = torch.empty(M, dtype=torch.float64, device="cuda")
+    nb = torch.empty(N, dtype=torch.float64, device="cuda")
+    sa = torch.empty(M, dtype=torch.float64, device="cuda")
+    sb = torch.empty(N, dtype=torch.float64, device="cuda")
+    handle.check(lib.mcd_standardize_ozaki(h, d_r.data_ptr(), M, G, G, a8.data_ptr(), nsl, sa.data_ptr(), na.data_ptr()))
+    handle.check(lib.mcd_standardize_ozaki(h, d_d.data_ptr(), N, G, G, b8.data_ptr(), nsl, sb.data_ptr(), nb.data_ptr()))
+    ldc, ldct = N + 2, M + 2
+    c = torch.full((M, ldc), 7.0, dtype=torch.float64, device="cuda")
+    ct = torch.full((N, ldct), 7.0, dtype=torch.float64, device="cuda")
+    handle.check(lib.mcd_corr_ozaki(h, a8.data_ptr(), M, b8.data_ptr(), N, G, ldk, nsl, sa.data_ptr(), sb.data_ptr(),
+                                    na.data_ptr(), nb.data_ptr(), c.data_ptr() if with_c else None, ldc,
+                                    ct.data_ptr() if with_ct else None, ldct))
+    handle.synchronize()
+    return c.cpu().numpy(), ct.cpu().numpy(), a8.cpu().numpy(), sa.cpu().numpy(), na.cpu().numpy()
+
+
+@pytest.mark.parametrize("nsl", [4, 6, 8])
+def test_ozaki_digits_reconstruct_unit_rows(handle, nsl):
+    from oracle import restatement as R
+
+    rng = np.random.default_rng(3)
+    x = np.log1p(rng.poisson(4.0, size=(50, 777)).astype(np.float64))
+    x[7] = 1.0  # zero-variance cell: all digits zero
+    _, _, a8, sa, na = _corr_ozaki(handle, x, x[:5].copy(), nsl)
+    xc, nrm = R.standardise(x)
+    unit = np.divide(xc, nrm[:, None], out=np.zeros_like(xc), where=nrm[:, None] > 0)
+    assert a8.min() >= -64 and a8.max() <= 63
+    q = np.zeros(a8.shape[1:], dtype=np.float64)
+    for t in range(nsl):
+        q = q * 128.0 + a8[t].astype(np.float64)
+    rec = q[:, :777] * 2.0 ** -(7 * nsl - 1) * sa[:, None]
+    # resolution: half a unit of the last digit, relative to the row scale
+    tol = 2.0 ** -(7 * nsl - 1) * sa.max()
+    assert np.abs(rec - unit).max() <= max(tol, 4e-16)
+    assert (a8[:, :, 777:] == 0).all()
+    assert (a8[:, 7, :] == 0).all()
+    assert np.abs(na - nrm).max() <= 1e-12 * nrm.max()
+    # the row scaling puts the largest digit vector entry in [0.25, 0.5)
+    live = nrm > 0
+    top = np.abs(q[live]).max(axis=1) * 2.0 ** -(7 * nsl - 1)
+    assert (top >= 0.25 - 1e-9).all() and (top < 0.5).all()
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 6), (128, 256, 64), (130, 257, 100), (300, 200, 1000), (515, 700, 4099),
+                                   (1000, 249, 20000)])
+def test_corr_ozaki_kernel(handle, shape):
+    from oracle import restatement as R
+
+    M, N, G = shape
+    rng = np.random.default_rng(M + 3 * N)
+    rna = np.log1p(rng.poisson(4.0, size=(M, G)).astype(np.float64))
+    dna = np.log1p(rng.integers(1, 5, size=(N, G)) * (1 + 0.05 * rng.standard_normal((N, G))))
+    if N > 2:
+        dna[1] = 2.0
+    ref = R.correlation_matrix(rna, dna)
+    for nsl, tol in ((6, 1e-10), (8, 1e-13), (5, 1e-8)):
+        c, ct, _, _, _ = _corr_ozaki(handle, rna, dna, nsl)
+        err = np.abs(c[:, :N] - ref).max()
+        print("ozaki int8 x%d max |dcorr| for" % nsl, shape, "=", err)
+        assert err < tol
+        assert (c[:, N:] == 7.0).all() and (ct[:, M:] == 7.0).all()
+        assert (ct[:, :M] == c[:, :N].T).all()
+        if N > 2:
+            assert (c[:, 1] == 0).all()
+
+
+def test_corr_ozaki_single_output(handle):
+    """Only C or only C^T requested: the pass partials then live in the one that exists."""
+    from oracle import restatement as R
+
+    rng = np.random.default_rng(11)
+    rna = rng.standard_normal((300, 500))
+    dna = rng.standard_normal((270, 500))
+    ref = R.correlation_matrix(rna, dna)
+    c, ct, _, _, _ = _corr_ozaki(handle, rna, dna, 6, with_ct=False)
+    assert np.abs(c[:, :270] - ref).max() < 1e-10 and (ct == 7.0).all()
+    c, ct, _, _, _ = _corr_ozaki(handle, rna, dna, 6, with_c=False)
+    assert np.abs(ct[:, :300] - ref.T).max() < 1e-10 and (c == 7.0).all()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
+def test_whole_path_ozaki(handle, name):
+    from conftest import tie_report
+    from macrodna_b200 import synth
+    from oracle import restatement as R
+
+    inst = synth.make_config_arrays(name)
+    M, G = inst.rna.shape
+    N = inst.dna.shape[0]
+    corr = np.empty((M, N))
+    assign, step, objs, stats = handle.cell2cell(inst.rna, inst.dna, M, N, G, precision="ozaki", corr_out=corr)
+    c_ref, a_ref, s_ref, o_ref = R.cell2cell_arrays(inst.rna, inst.dna)
+    err = np.abs(corr - c_ref).max()
+    print(name, "ozaki: max |dcorr| %.3g" % err)
+    assert err < 1e-10
+    ident, rep = tie_report(c_ref, assign, step, a_ref, s_ref, rel=1e-9)
+    assert ident, rep
+    assert np.abs(objs - o_ref).max() <= 1e-9 * np.abs(o_ref).max()
