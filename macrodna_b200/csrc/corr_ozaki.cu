@@ -157,6 +157,7 @@ struct OzParams {
   int64_t ldc;
   double* Ct;
   int64_t ldct;
+  unsigned int* wave_counter;  // zeroed before the launch
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -207,7 +208,24 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int u = 0;
       uint32_t phase = 0;
+      unsigned int wave_target = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        // Wave alignment.  The ~74 pair tiles of a wave share 8 RNA and ~9 DNA panels, but only the k-window all
+        // of them are currently working in fits L2 (1.8 MB of distinct digits per k-block).  Free-running pairs
+        // drift apart over the waves and every pair then streams its panels from HBM by itself (ncu: 755 GB of
+        // DRAM reads, L2 hit rate 45 %).  So the leaders' producers start each wave together; inside a wave the
+        // pairs keep each other in step (whoever is ahead takes the DRAM misses, the others hit L2 and catch up).
+        // All CTAs are co-resident (grid <= #SMs, 1 CTA/SM), so the spin cannot deadlock.
+        if (leader && tile != pair) {
+          const int wave = (tile - pair) / num_pairs;
+          wave_target += (unsigned int)min(num_pairs, num_tiles - wave * num_pairs);
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_counter) : "memory");
+          unsigned int seen;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_counter) : "memory");
+            if ((int)(seen - wave_target) < 0) __nanosleep(200);
+          } while ((int)(seen - wave_target) < 0);
+        }
         int tm, tn;
         decode_tile(tile, p.tiles_m, p.tiles_n, tm, tn);
         const int row0 = tm * TM + (int)cta_rank * HALF;
@@ -413,6 +431,8 @@ int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int
   p.ldc = ldc;
   p.Ct = Ct;
   p.ldct = ldct;
+  p.wave_counter = reinterpret_cast<unsigned int*>(h->d_flags + 8);
+  MCD_CUDA(h, cudaMemsetAsync(p.wave_counter, 0, sizeof(unsigned int), h->stream));
   MCD_CUDA(h, cudaFuncSetAttribute(corr_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   const int64_t max_pairs = h->sm_count / 2;

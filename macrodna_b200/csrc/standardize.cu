@@ -63,16 +63,13 @@ __device__ __forceinline__ double group_max(double v, double* red) {
 //   q = sum_t d_t * 128^(nsl-1-t)      (t = 0 is the most significant slice).
 // The products of two such digit vectors are exact in the tensor core's int32 accumulators.
 __device__ __forceinline__ void ozaki_digits(double y, int nsl, int d[MCD_OZAKI_MAX_SLICES]) {
-  long long q = __double2ll_rn(scalbn(y, 7 * nsl - 1));
+  const long long q = __double2ll_rn(scalbn(y, 7 * nsl - 1));  // |q| <= 2^(7 nsl - 2)
+  // Adding 64 to every 7-bit field turns the balanced digits into plain bit fields: q + B = sum (d_t + 64) 128^..
+  const unsigned long long B = (0x0102040810204081ull << 6) & ((1ull << (7 * nsl)) - 1ull);
+  const unsigned long long qb = (unsigned long long)q + B;
 #pragma unroll
-  for (int t = MCD_OZAKI_MAX_SLICES - 1; t >= 0; --t) {
-    d[t] = 0;
-    if (t < nsl) {
-      const int r = (int)((q + 64) & 127) - 64;
-      d[t] = r;
-      q = (q - r) >> 7;
-    }
-  }
+  for (int t = 0; t < MCD_OZAKI_MAX_SLICES; ++t)
+    d[t] = (t < nsl) ? (int)((qb >> (7 * (nsl - 1 - t))) & 127ull) - 64 : 0;
 }
 
 // Split-precision operand for the tcgen05 path: y (|y| <= 1, a unit-norm centred value) is scaled by
