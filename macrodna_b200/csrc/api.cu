@@ -765,6 +765,17 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
 
   int bad = 0;
   if (stats) memset(stats, 0, sizeof *stats);
+  if (getenv("MCD_LAP_DEBUG")) {
+    int64_t R = M;
+    for (int64_t s = 0; s < nsteps; ++s, R -= N) {
+      const int64_t mm = R > N ? R : N;
+      fprintf(stderr, "[lap step %lld] n=%lld m=%lld rounds=%lld bids=%lld sweeps=%lld aug=%lld/%lld cyc=", (long long)s,
+              (long long)(R > N ? N : R), (long long)mm, hc[s].rounds, hc[s].bids, hc[s].bytes / (mm * 8), hc[s].aug_rows,
+              hc[s].aug_steps);
+      for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].t_phase[q]);
+      fprintf(stderr, "\n");
+    }
+  }
   for (int64_t s = 0; s < nsteps; ++s) {
     if (hc[s].status) bad = 1;
     if (stats) {

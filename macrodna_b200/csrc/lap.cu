@@ -387,7 +387,8 @@ __device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int 
 }
 
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
-                                                                  int tail_nu, int use_lists, int list_min_nu) {
+                                                                  int tail_nu, int use_lists, int list_min_nu,
+                                                                  int aug_nu) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || s.flags[0]) return;  // uniform: written only at the very end of earlier launches
   const int first_phase = phase_idx == 0;
@@ -434,7 +435,9 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
   int nu = s.n;
   bool stalled = false;
 
-  while (nu > tail_nu) {
+  // the exact (eps = 0) phase may hand its last aug_nu persons straight to the augmenting-path kernel
+  const int stop_nu = (eps == 0.0 && aug_nu > tail_nu) ? aug_nu : tail_nu;
+  while (nu > stop_nu) {
     if (rounds >= s.max_rounds) {
       guard_hit = true;
       break;
@@ -613,9 +616,10 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     const bool aborted = stalled || guard_hit;
     if (eps == 0.0) {
       // final phase: either done, or the narrow kernel finishes it, or the augmentation kernel must
-      ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
-      ctrl->stalled = (aborted && nu > 0) ? 1 : 0;
-      ctrl->finished = (aborted || nu == 0) ? 1 : 0;
+      const bool to_aug = !aborted && nu > 0 && nu <= aug_nu;
+      ctrl->in_tail = (!aborted && nu > 0 && !to_aug) ? 1 : 0;
+      ctrl->stalled = ((aborted || to_aug) && nu > 0) ? 1 : 0;
+      ctrl->finished = (aborted || nu == 0 || to_aug) ? 1 : 0;
     } else {
       // scaling phase: its only product is the price vector; a guard hit just ends it early
       ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
@@ -1474,9 +1478,11 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     if (v >= 0 && v < tail_nu) tail_nu = v;
   }
 
+  int aug_nu = (e = getenv("MCD_LAP_AUG_NU")) ? atoi(e) : 0;
+  if (n == m && (e = getenv("MCD_LAP_AUG_NU_SQUARE"))) aug_nu = atoi(e);
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
-    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu};
+    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                             h->stream));
     h->launches++;
