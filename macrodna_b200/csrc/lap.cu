@@ -118,6 +118,7 @@ struct LapState {
   double* pv2;
   int* pj1;
   int* pj2;
+  double* pbound;            // [grid slots] chunk bounds of cooperative list rebuilds
   // augmentation scratch
   double* sp;                // [m] shortest path cost
   int* pred;                 // [m]
@@ -323,6 +324,113 @@ __device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* c
 }
 
 
+// One CHUNK [j0, j1) of a row sweep that rebuilds person i's candidate list cooperatively: nch CTAs each sweep
+// one chunk and contribute their chunk's top kc = list_k / nch objects to the list slots [c*kc, (c+1)*kc) plus a
+// chunk bound (no object of the chunk outside those kc is worth more).  The list is then the union of the chunk
+// tops (not the global top-128, but every unlisted object is still below max_c bound_c, which is all the
+// certificate needs).  Returns the chunk's exact top-2 in every thread; *bound_out is valid in every thread.
+template <int NT>
+__device__ Top2 chunk_scan_build(const LapState& s, int i, int j0, int j1, int c, int kc, double* cand_v, int* cand_j,
+                                 double* red, double* bound_out) {
+  constexpr int NC = NT * CAND_T;
+  const int tid = threadIdx.x;
+  const double* w = s.W + (int64_t)i * s.ldw;
+  double tv[CAND_T];
+  int tj[CAND_T];
+#pragma unroll
+  for (int q = 0; q < CAND_T; ++q) tv[q] = NEG_INF, tj[q] = 0x7fffffff;
+  double lb = NEG_INF;
+  auto push = [&](double v, int j) {
+    if (better(v, j, tv[CAND_T - 1], tj[CAND_T - 1])) {
+      lb = fmax(lb, tv[CAND_T - 1]);
+      tv[CAND_T - 1] = v;
+      tj[CAND_T - 1] = j;
+#pragma unroll
+      for (int q = CAND_T - 1; q > 0; --q) {
+        if (better(tv[q], tj[q], tv[q - 1], tj[q - 1])) {
+          const double xv = tv[q];
+          tv[q] = tv[q - 1];
+          tv[q - 1] = xv;
+          const int xj = tj[q];
+          tj[q] = tj[q - 1];
+          tj[q - 1] = xj;
+        }
+      }
+    } else {
+      lb = fmax(lb, v);
+    }
+  };
+  if (s.vec) {  // j0 is even
+    constexpr int S = 2 * NT;
+    int j = j0 + 2 * tid;
+    for (; j + 3 * S + 1 < j1; j += 4 * S) {
+      double2 wv[4], pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(w + j + u * S));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pv[u] = ldm(reinterpret_cast<const double2*>(s.price + j + u * S));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        push(wv[u].x - pv[u].x, j + u * S);
+        push(wv[u].y - pv[u].y, j + u * S + 1);
+      }
+    }
+    for (; j < j1; j += S) {
+      push(__ldg(w + j) - ldm(s.price + j), j);
+      if (j + 1 < j1) push(__ldg(w + j + 1) - ldm(s.price + j + 1), j + 1);
+    }
+  } else {
+    for (int j = j0 + tid; j < j1; j += NT) push(__ldg(w + j) - ldm(s.price + j), j);
+  }
+#pragma unroll
+  for (int q = 0; q < CAND_T; ++q) {
+    cand_v[tid * CAND_T + q] = tv[q];
+    cand_j[tid * CAND_T + q] = tj[q];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lb;
+  __syncthreads();
+  for (int k = 2; k <= NC; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = tid; idx < NC; idx += NT) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const double va = cand_v[idx], vb = cand_v[ixj];
+          const int ja = cand_j[idx], jb = cand_j[ixj];
+          const bool a_first = better(va, ja, vb, jb);
+          const bool desc = (idx & k) == 0;
+          if (desc ? !a_first : a_first) {
+            cand_v[idx] = vb;
+            cand_v[ixj] = va;
+            cand_j[idx] = jb;
+            cand_j[ixj] = ja;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  double bound = NEG_INF;
+#pragma unroll
+  for (int q = 0; q < NT / 32; ++q) bound = fmax(bound, red[q]);
+  bound = fmax(bound, cand_v[kc]);  // kc < NC always (kc <= LIST_K < NC)
+  for (int q = tid; q < kc; q += NT) {
+    const int j = cand_j[q];
+    const bool real = j != 0x7fffffff;  // chunks shorter than kc pad their slots with a never-chosen entry
+    s.lj[(int64_t)i * LIST_K + c * kc + q] = real ? j : j0;
+    s.lw[(int64_t)i * LIST_K + c * kc + q] = real ? __ldg(w + j) : NEG_INF;
+  }
+  Top2 t;
+  t.v1 = cand_v[0];
+  t.j1 = cand_j[0] == 0x7fffffff ? -1 : cand_j[0];
+  t.v2 = cand_v[1];
+  t.j2 = cand_j[1] == 0x7fffffff ? -1 : cand_j[1];
+  *bound_out = bound;
+  __syncthreads();
+  return t;
+}
+
 // Plain row sweep (no candidate list): exact top-2 of W[i,:] - price by an NT-thread CTA.  Used for the
 // square (eps-scaling) problems, where every price inflates and lists would be rebuilt on every bid.
 template <int NT>
@@ -459,16 +567,62 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
         }
       }
       grid.sync();
-      // ---- stage 2: one CTA per failed bidder sweeps its row and rebuilds the list (balanced over the grid)
+      // ---- stage 2: failed lists are rebuilt by row sweeps.  With at least a grid-full of failures one CTA
+      //      sweeps one row; with fewer, every row is split over nch CTAs (chunk_scan_build) so that a round
+      //      costs one memory latency instead of one CTA streaming a whole row by itself.
       const int nfail = ldm(&ctrl->nfail[parity]);
       if (gtid == 0) ctrl->nfail[parity ^ 1] = 0;
-      for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
-        const int kk = ldm(&s.fail[f]);
-        const int i = ldm(&un[kk]);
-        const Top2 t = full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
-        if (tid == 0) {
-          wide_finalize_bid(s, kk, i, t, eps);
-          sweeps++;
+      int nch = 1;
+      if (nfail > 0 && s.list_k == LIST_K) {
+        while (nch < 16 && 2 * nch * nfail <= (int)gridDim.x && s.m / (2 * nch) >= 1024) nch *= 2;
+      }
+      if (nch == 1) {
+        for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
+          const int kk = ldm(&s.fail[f]);
+          const int i = ldm(&un[kk]);
+          const Top2 t = full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
+          if (tid == 0) {
+            wide_finalize_bid(s, kk, i, t, eps);
+            sweeps++;
+          }
+        }
+      } else {
+        const int kc = LIST_K / nch;
+        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
+        const int items = nfail * nch;  // <= gridDim.x
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+          const int f = item / nch, c = item - f * nch;
+          const int kk = ldm(&s.fail[f]);
+          const int i = ldm(&un[kk]);
+          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
+          double cb;
+          const Top2 t = chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
+          if (tid == 0) {
+            s.pv1[item] = t.v1;
+            s.pv2[item] = t.v2;
+            s.pj1[item] = t.j1;
+            s.pj2[item] = t.j2;
+            s.pbound[item] = cb;
+            int prev;  // release: partials and list slots above are visible before the count
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[kk]) : "memory");
+            if (prev == nch - 1) {
+              Top2 a{NEG_INF, NEG_INF, -1, -1};
+              double bound = NEG_INF;
+              for (int cc = 0; cc < nch; ++cc) {
+                const int sl = f * nch + cc;
+                Top2 b{__ldcg(&s.pv1[sl]), __ldcg(&s.pv2[sl]), __ldcg(&s.pj1[sl]), __ldcg(&s.pj2[sl])};
+                if (b.j1 >= 0) top2_push(a, b.v1, b.j1);
+                if (b.j2 >= 0) top2_push(a, b.v2, b.j2);
+                bound = fmax(bound, __ldcg(&s.pbound[sl]));
+              }
+              s.done[kk] = 0;
+              s.lbound[i] = bound;
+              s.lvalid[i] = 1;
+              wide_finalize_bid(s, kk, i, a, eps);
+            }
+            if (c == 0) sweeps++;
+          }
+          __syncthreads();
         }
       }
     } else {
@@ -1115,6 +1269,370 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
 }
 
 // ------------------------------------------------------------------------------------------------
+// Phase A, narrow part, MASTER / HELPER form (long rows and the square phases).
+//
+// Measured on the 10k x 50k steps: a person's top-128 candidate list certifies ~90 % of its bids, and the ~25k
+// narrow rounds of a step are one dependent chain -- what matters is the latency of ONE round.  So CTA 0 of a
+// cluster (the master) runs the rounds by itself: one warp per bidder reads the bidder's list (L1/L2 resident:
+// the same few persons bid over and over), gathers the prices of its 128 candidates, reduces to the top-2 and
+// checks the certificate; the winners are resolved in shared memory and applied to the global state, which only
+// the master writes while this kernel runs.  No cluster traffic at all in such a round (~0.5 us instead of ~7 us
+// for the scan-every-row cluster kernel above).
+// Only when a list FAILS does the cluster work: the master fences its price updates, posts the row to every CTA
+// (st.async + mbarrier complete_tx), each CTA sweeps its slice of the row (W from HBM, prices from L2), keeps its
+// slice's top KC = 128 / #CTAs objects plus a slice bound, and ships them back into the master's shared memory
+// the same way.  The union of the slice tops IS the person's new list (every unlisted object lies below
+// max_c bound_c, which is all the certificate needs, and the row's true top-2 are always in it).
+// ------------------------------------------------------------------------------------------------
+constexpr int MH_NU = 32;           // bidders per round the master takes (one warp resolves them)
+constexpr int MH_KW = 4;            // candidates every warp hands to its CTA's selection
+constexpr uint32_t MH_CMD_BYTES = 16;
+
+struct __align__(16) MhEntry {  // one list entry travelling from a helper to the master
+  double w;                     // cost W[i, j]
+  int j, pad;
+};
+
+// warp-wide arg-max of (v, j) with the smaller index winning ties; every lane returns the winner
+__device__ __forceinline__ void warp_argmax(double& v, int& j) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+    if (ov > v || (ov == v && (unsigned)oj < (unsigned)j)) {
+      v = ov;
+      j = oj;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s, int mc /* objects per CTA, even */) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished || !ctrl->in_tail || s.flags[0]) return;  // uniform over the cluster
+  uint32_t cta, ncta;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(ncta));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int kc = LIST_K / (int)ncta;  // list slots every CTA fills (8 for 16 CTAs, 16 for 8)
+
+  __shared__ __align__(16) MhEntry s_reply[LIST_K];      // master: [cta][kc] entries of the rebuilt list
+  __shared__ __align__(16) double s_rbound[2 * CL_MAX_CS];  // master: slice bounds (16-byte slots)
+  __shared__ __align__(16) int s_cmd[4];                  // every CTA: {row, type, -, -} posted by the master
+  __shared__ __align__(8) unsigned long long s_bars[2];   // [0] command arrived (every CTA), [1] replies in (master)
+  __shared__ double s_cv[TAIL_WARPS * MH_KW];
+  __shared__ int s_cj[TAIL_WARPS * MH_KW];
+  __shared__ double s_wb[TAIL_WARPS];
+  __shared__ int s_list[2][MH_NU];
+  __shared__ int s_bj[MH_NU];
+  __shared__ double s_gam[MH_NU], s_bval[MH_NU];
+  __shared__ unsigned long long s_key[MH_NU];
+  __shared__ int s_fail[MH_NU];
+  __shared__ int s_cnt[4];  // [0] failures, [1] next count, [2] accepted
+  const uint32_t bar_cmd = smem_addr(&s_bars[0]), bar_reply = smem_addr(&s_bars[1]);
+
+  const int o0 = min(s.m, (int)cta * mc), o1 = min(s.m, o0 + mc);
+  const int cur_list = ctrl->cur;
+  int nu = ctrl->cnt[cur_list];
+  const double eps = ctrl->eps;
+  if (tid < MH_NU) s_list[0][tid] = tid < nu ? s.un[cur_list][tid] : -1;
+  if (tid == 0) {
+    tail_mbar_init(bar_cmd, 1);
+    tail_mbar_init(bar_reply, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tail_mbar_expect(bar_cmd, MH_CMD_BYTES);
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t reply0 = map_to_cta(smem_addr(s_reply), 0);
+  const uint32_t rbound0 = map_to_cta(smem_addr(s_rbound), 0);
+  const uint32_t bar_reply0 = map_to_cta(bar_reply, 0);
+
+  // Sweep this CTA's slice of row i: slice top-kc (+ bound) to the master.  Called by all threads of every CTA.
+  auto sweep_slice = [&](int i) {
+    const double* wrow = s.W + (int64_t)i * s.ldw;
+    Top2 t{NEG_INF, NEG_INF, -1, -1};
+    double lb = NEG_INF;  // largest value this lane dropped
+    auto push = [&](double v, int j) {
+      if (v > t.v1) {
+        lb = fmax(lb, t.v2);
+        t.v2 = t.v1, t.j2 = t.j1, t.v1 = v, t.j1 = j;
+      } else if (v > t.v2) {
+        lb = fmax(lb, t.v2);
+        t.v2 = v, t.j2 = j;
+      } else {
+        lb = fmax(lb, v);
+      }
+    };
+    int j = o0 + 2 * tid;
+    if (s.vec) {
+      constexpr int S = 2 * TAIL_THREADS;
+      for (; j + 3 * S + 1 < o1; j += 4 * S) {
+        double2 wv[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + j + u * S));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pv[u] = ldm(reinterpret_cast<const double2*>(s.price + j + u * S));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          push(wv[u].x - pv[u].x, j + u * S);
+          push(wv[u].y - pv[u].y, j + u * S + 1);
+        }
+      }
+      // remainder: up to 4 more pairs per lane, all loads issued before the first use
+      double2 wv[4], pv[4];
+      bool full[4], half[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u * S;
+        full[u] = jj + 1 < o1;
+        half[u] = !full[u] && jj < o1;
+        wv[u] = make_double2(0.0, 0.0);
+        pv[u] = make_double2(0.0, 0.0);
+        if (full[u]) {
+          wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + jj));
+          pv[u] = ldm(reinterpret_cast<const double2*>(s.price + jj));
+        } else if (half[u]) {
+          wv[u].x = __ldg(wrow + jj);
+          pv[u].x = ldm(s.price + jj);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u * S;
+        if (full[u] || half[u]) push(wv[u].x - pv[u].x, jj);
+        if (full[u]) push(wv[u].y - pv[u].y, jj + 1);
+      }
+    } else {
+      for (int jj = o0 + tid; jj < o1; jj += TAIL_THREADS) push(__ldg(wrow + jj) - ldm(s.price + jj), jj);
+    }
+    // warp: hand the warp's best MH_KW candidates to the CTA, everything else goes into the warp bound
+#pragma unroll
+    for (int r = 0; r < MH_KW; ++r) {
+      double bv = t.v1;
+      int bj = t.j1;
+      warp_argmax(bv, bj);
+      if (bj >= 0 && bj == t.j1) {  // this lane held the winner: pop it
+        t.v1 = t.v2, t.j1 = t.j2;
+        t.v2 = NEG_INF, t.j2 = -1;
+      }
+      if (lane == r) {
+        s_cv[warp * MH_KW + r] = bv;
+        s_cj[warp * MH_KW + r] = bj;
+      }
+    }
+    double wb = fmax(lb, t.v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wb = fmax(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+    if (lane == 0) s_wb[warp] = wb;
+    __syncthreads();
+    // warp 0: the CTA's best kc of the TAIL_WARPS * MH_KW = 64 candidates (two per lane)
+    if (warp == 0) {
+      double a1 = s_cv[lane], a2 = s_cv[lane + 32];
+      int b1 = s_cj[lane], b2 = s_cj[lane + 32];
+      if (b1 < 0) a1 = NEG_INF;
+      if (b2 < 0) a2 = NEG_INF;
+      if (a2 > a1 || (a2 == a1 && (unsigned)b2 < (unsigned)b1)) {
+        const double xa = a1;
+        a1 = a2, a2 = xa;
+        const int xb = b1;
+        b1 = b2, b2 = xb;
+      }
+      double ev = NEG_INF;
+      int ej = -1;
+      for (int r = 0; r < kc; ++r) {
+        double bv = a1;
+        int bj = b1;
+        warp_argmax(bv, bj);
+        if (bj >= 0 && bj == b1) {
+          a1 = a2, b1 = b2;
+          a2 = NEG_INF, b2 = -1;
+        }
+        if (lane == r) ev = bv, ej = bj;
+      }
+      double cb = fmax(a1, lane < TAIL_WARPS ? s_wb[lane] : NEG_INF);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cb = fmax(cb, __shfl_xor_sync(0xffffffffu, cb, o));
+      if (lane < kc) {
+        // empty slots (slice shorter than kc) become never-chosen entries on a valid object index
+        const double wv = ej >= 0 ? __ldg(wrow + ej) : NEG_INF;
+        const int jv = ej >= 0 ? ej : 0;
+        st_async_v2(reply0 + (uint32_t)((cta * kc + lane) * sizeof(MhEntry)), (uint64_t)__double_as_longlong(wv),
+                    (uint64_t)(uint32_t)jv, bar_reply0);
+      }
+      if (lane == 0) st_async_v2(rbound0 + cta * 16, (uint64_t)__double_as_longlong(cb), 0ull, bar_reply0);
+    }
+    __syncthreads();  // s_cv / s_cj / s_wb are free again
+  };
+
+  if (cta != 0) {
+    // ===================== helpers: sleep on the command barrier =====================
+    uint32_t par = 0;
+    for (;;) {
+      tail_mbar_wait(bar_cmd, par);
+      par ^= 1;
+      const int row = s_cmd[0], type = s_cmd[1];
+      __syncthreads();  // everybody has the command before the barrier is re-armed
+      if (tid == 0) tail_mbar_expect(bar_cmd, MH_CMD_BYTES);
+      if (type != 0) break;
+      sweep_slice(row);
+    }
+  } else {
+    // ===================== master =====================
+    long long rounds = 0, bids = 0, sweeps = 0;
+    long long tq[4] = {0, 0, 0, 0};
+    int cur = 0, stalled = 0;
+    uint32_t rpar = 0;
+    const uint32_t reply_bytes = ncta * (uint32_t)(kc * sizeof(MhEntry) + 16);
+
+    auto finalize = [&](int b, Top2 t) {  // one thread records bidder b's bid in shared memory
+      int j = t.j1;
+      if (eps == 0.0 && t.j2 >= 0 && t.v1 == t.v2 && s.owner[j] >= 0 && s.owner[t.j2] < 0) j = t.j2;  // exact tie
+      const double gamma = (t.j2 >= 0 ? (t.v1 - t.v2) : 0.0) + eps;
+      s_bj[b] = j;
+      s_gam[b] = gamma;
+      s_bval[b] = (j == t.j1) ? t.v1 : t.v2;
+      s_key[b] = pack_bid(gamma, s_list[cur][b]);
+    };
+
+    while (nu > 0) {
+      if (rounds >= s.max_rounds) {
+        stalled = 1;
+        break;
+      }
+      const long long c0 = clock64();
+      if (tid == 0) s_cnt[0] = 0;
+      __syncthreads();
+      // ---- 1. bids from the candidate lists, one warp per bidder (at most two bidders per warp)
+      for (int b = warp; b < nu; b += TAIL_WARPS) {
+        const int i = s_list[cur][b];
+        bool ok = false;
+        Top2 t;
+        if (s.lvalid[i]) ok = list_bid<false>(s, i, lane, t);
+        if (lane == 0) {
+          if (ok)
+            finalize(b, t);
+          else
+            s_fail[atomicAdd(&s_cnt[0], 1)] = b;
+        }
+      }
+      __syncthreads();
+      const long long c1 = clock64();
+      // ---- 2. failed lists: the whole cluster sweeps the row, the master takes the new list
+      const int nfail = s_cnt[0];
+      for (int f = 0; f < nfail; ++f) {
+        const int b = s_fail[f];
+        const int i = s_list[cur][b];
+        if (s.list_k == s.m) {  // short rows: the list is simply every object
+          for (int e = tid; e < s.m; e += TAIL_THREADS) {
+            s.lj[(int64_t)i * LIST_K + e] = e;
+            s.lw[(int64_t)i * LIST_K + e] = s.W[(int64_t)i * s.ldw + e];
+          }
+          if (tid == 0) s.lbound[i] = NEG_INF, s.lvalid[i] = 1;
+          __syncthreads();
+        } else {
+          if (tid == 0) {
+            __threadfence();  // the helpers read prices from L2: every update of the earlier rounds is there first
+            tail_mbar_expect(bar_reply, reply_bytes);
+          }
+          __syncthreads();
+          if (tid >= 1 && tid < (int)ncta)
+            st_async_v2(map_to_cta(smem_addr(s_cmd), tid), (uint64_t)(uint32_t)i, 0ull, map_to_cta(bar_cmd, tid));
+          sweep_slice(i);
+          tail_mbar_wait(bar_reply, rpar);
+          rpar ^= 1;
+          if (tid < LIST_K) {
+            s.lj[(int64_t)i * LIST_K + tid] = s_reply[tid].j;
+            s.lw[(int64_t)i * LIST_K + tid] = s_reply[tid].w;
+          }
+          if (tid == 0) {
+            double bound = NEG_INF;
+            for (uint32_t c = 0; c < ncta; ++c) bound = fmax(bound, s_rbound[2 * c]);
+            s.lbound[i] = bound;
+            s.lvalid[i] = 1;
+          }
+          __syncthreads();  // list + bound visible to warp 0 below; s_reply may be overwritten by the next sweep
+        }
+        if (warp == 0) {
+          Top2 t;
+          list_bid<false>(s, i, lane, t);  // the fresh list holds the row's true top-2
+          if (lane == 0) finalize(b, t);
+        }
+      }
+      sweeps += nfail;
+      __syncthreads();
+      const long long c2 = clock64();
+      // ---- 3. resolution by warp 0 (nu <= 32)
+      if (warp == 0) {
+        int person_out = -1;
+        bool applied = false;
+        if (lane < nu) {
+          const int i = s_list[cur][lane];
+          const int j = s_bj[lane];
+          const unsigned long long key = s_key[lane];
+          bool win = true;
+          for (int q = 0; q < nu; ++q)
+            if (s_bj[q] == j && s_key[q] > key) win = false;
+          person_out = i;  // re-queue unless the bid is applied
+          if (win) {
+            const double p_old = s.price[j];
+            const double p_new = p_old + s_gam[lane];
+            const int prev = s.owner[j];
+            if (prev < 0 || p_new > p_old) {
+              applied = true;
+              person_out = prev;  // the evicted owner (or -1) bids next round
+              s.owner[j] = i;
+              s.price[j] = p_new;
+              s.col4row[i] = j;
+              s.profit[i] = (s_bval[lane] + p_old) - p_new;
+              if (prev >= 0) s.col4row[prev] = -1;
+            }
+          }
+        }
+        const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+        const unsigned acc = __ballot_sync(0xffffffffu, applied);
+        if (person_out >= 0) s_list[cur ^ 1][__popc(has & ((1u << lane) - 1u))] = person_out;
+        if (lane == 0) s_cnt[1] = __popc(has), s_cnt[2] = __popc(acc);
+      }
+      __syncthreads();
+      const int nu_next = s_cnt[1], accepted = s_cnt[2];
+      rounds++;
+      bids += nu;
+      const long long c3 = clock64();
+      tq[0] += c1 - c0;
+      tq[1] += c2 - c1;
+      tq[2] += c3 - c2;
+      cur ^= 1;
+      nu = nu_next;
+      if (accepted == 0 && nu > 0) {  // nobody could raise a price: exact ties -> augmentation kernel
+        stalled = 1;
+        break;
+      }
+    }
+    // release the helpers
+    __syncthreads();
+    if (tid >= 1 && tid < (int)ncta)
+      st_async_v2(map_to_cta(smem_addr(s_cmd), tid), (uint64_t)1 << 32, 0ull, map_to_cta(bar_cmd, tid));
+    if (tid < nu) s.un[cur_list][tid] = s_list[cur][tid];
+    if (tid == 0) {
+      ctrl->cnt[cur_list] = nu;
+      ctrl->in_tail = 0;
+      if (eps == 0.0) {
+        ctrl->finished = 1;
+        ctrl->stalled = (stalled && nu > 0) ? 1 : 0;
+      }
+      s.counters->rounds += rounds;
+      s.counters->bids += bids;
+      s.counters->bytes += sweeps * (long long)s.m * 8;
+      for (int q = 0; q < 4; ++q) s.counters->t_phase[4 + q] += tq[q];
+    }
+  }
+  // no CTA may leave while peers can still address its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // Phase B: shortest augmenting paths for the persons phase A left unassigned.  One CTA; the
 // per-step work is one cost row (m objects) spread over 1024 threads.  min-form duals:
 // u_i = -profit_i, v_j = -price_j, cost' = -W.
@@ -1351,7 +1869,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up(n * LIST_K * 8, 256);   // lw
   b += align_up(n * 8, 256);            // lbound
   b += 3 * align_up(n * 4, 256);        // lvalid, fail, done
-  b += 2 * align_up(MAX_GRID_SLOTS * 8, 256) + 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // split-row partials
+  b += 3 * align_up(MAX_GRID_SLOTS * 8, 256) + 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // split-row partials
   b += align_up(m * 8, 256);            // sp
   b += align_up(m * 4, 256);            // pred
   b += align_up((n + 1) * 4, 256);      // sc_col
@@ -1397,6 +1915,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.pv2 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
   s.pj1 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
   s.pj2 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
+  s.pbound = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
   {
     const char* e2 = getenv("MCD_LAP_MIN_CHUNK");
     int min_chunk = e2 ? atoi(e2) : 4096;
@@ -1472,6 +1991,13 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     if (cs > 8)
       MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
+  const bool mh_tail = cluster_tail && !((e = getenv("MCD_LAP_TAIL_MH")) && atoi(e) == 0);
+  if (mh_tail && cs != 8 && cs != 16) cs = 16;
+  if (mh_tail) {
+    mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
+    if (cs > 8)
+      MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_mh_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
   int tail_nu = list_tail ? TAIL_NU : (cluster_tail ? CL_NU : 0);
   if ((e = getenv("MCD_LAP_TAIL_NU"))) {
     const int v = atoi(e);
@@ -1493,7 +2019,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(cs);
       cfg.blockDim = dim3(TAIL_THREADS);
-      cfg.dynamicSmemBytes = tail_smem;
+      cfg.dynamicSmemBytes = mh_tail ? 0 : tail_smem;
       cfg.stream = h->stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1502,7 +2028,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_cluster_kernel, s, mc));
+      if (mh_tail)
+        MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_mh_kernel, s, mc));
+      else
+        MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_cluster_kernel, s, mc));
       h->launches++;
     }
   }
