@@ -194,21 +194,37 @@ __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top
   const int K = s.list_k;
   const int* lj = s.lj + (int64_t)i * LIST_K;
   const double* lw = s.lw + (int64_t)i * LIST_K;
-  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  // everything that depends only on i is requested up front: the bid is two dependent memory latencies
+  // (list, then the prices of its objects), not four
+  const int valid = COHERENT ? ldm(&s.lvalid[i]) : s.lvalid[i];
+  const double b = COHERENT ? ldm(s.lbound + i) : s.lbound[i];
+  int js[LIST_K / 32];
+  double ws[LIST_K / 32];
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q) {
     const int e = lane + 32 * q;
+    js[q] = -1;
+    ws[q] = NEG_INF;
     if (e < K) {
-      const int j = COHERENT ? ldm(lj + e) : lj[e];
-      const double w = COHERENT ? ldm(lw + e) : lw[e];
-      const double p = COHERENT ? ldm(s.price + j) : s.price[j];
-      top2_push(t, w - p, j);
+      js[q] = COHERENT ? ldm(lj + e) : lj[e];
+      ws[q] = COHERENT ? ldm(lw + e) : lw[e];
     }
   }
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  out = t;
+  if (!valid) return false;  // never built: the slots hold garbage, do not touch them
+  double ps[LIST_K / 32];
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q) {
+    ps[q] = 0.0;
+    if (js[q] >= 0) ps[q] = COHERENT ? ldm(s.price + js[q]) : s.price[js[q]];
+  }
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q)
+    if (js[q] >= 0) top2_push(t, ws[q] - ps[q], js[q]);
   t = top2_warp_reduce(t);
   out = t;
   if (K == s.m) return true;  // every object is listed
-  const double b = COHERENT ? ldm(s.lbound + i) : s.lbound[i];
   return t.j2 >= 0 && t.v2 >= b;
 }
 
@@ -323,6 +339,128 @@ __device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* c
   return t;
 }
 
+
+// warp-wide arg-max of (v, j) with the smaller index winning ties; every lane returns the winner
+__device__ __forceinline__ void warp_argmax(double& v, int& j) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+    if (ov > v || (ov == v && (unsigned)oj < (unsigned)j)) {
+      v = ov;
+      j = oj;
+    }
+  }
+}
+
+// Same contract as chunk_scan_build below for kc <= 16 (many short chunks), without the shared-memory sort:
+// every lane keeps its top-2 and the largest value it dropped, every warp hands its best 4 to the CTA by four
+// shuffle arg-max rounds, warp 0 picks the chunk's kc from those NT/32 * 4 (<= 32) candidates.  Whatever a warp
+// or the CTA does not pass on only raises the bound, so the certificate stays valid (it is merely a little
+// weaker than the exact chunk top-kc).  All loads of a chunk of <= 8 * 2 * NT objects are issued before the
+// first use: a chunk costs one memory latency.
+template <int NT>
+__device__ Top2 chunk_scan_select(const LapState& s, int i, int j0, int j1, int c, int kc, double* s_cv, int* s_cj,
+                                  double* s_wb, double* bound_out) {
+  static_assert(NT / 32 * 4 <= 32, "one candidate per lane of warp 0");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* w = s.W + (int64_t)i * s.ldw;
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  double lb = NEG_INF;
+  auto push = [&](double v, int j) {
+    if (v > t.v1) {
+      lb = fmax(lb, t.v2);
+      t.v2 = t.v1, t.j2 = t.j1, t.v1 = v, t.j1 = j;
+    } else if (v > t.v2) {
+      lb = fmax(lb, t.v2);
+      t.v2 = v, t.j2 = j;
+    } else {
+      lb = fmax(lb, v);
+    }
+  };
+  if (s.vec) {  // j0 is even
+    constexpr int S = 2 * NT;
+    for (int j = j0 + 2 * tid; j < j1; j += 8 * S) {
+      double2 wv[8], pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j + u * S;
+        wv[u] = make_double2(NEG_INF, NEG_INF);
+        pv[u] = make_double2(0.0, 0.0);
+        if (jj + 1 < j1) {
+          wv[u] = __ldg(reinterpret_cast<const double2*>(w + jj));
+          pv[u] = ldm(reinterpret_cast<const double2*>(s.price + jj));
+        } else if (jj < j1) {
+          wv[u].x = __ldg(w + jj);
+          pv[u].x = ldm(s.price + jj);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j + u * S;
+        if (jj < j1) push(wv[u].x - pv[u].x, jj);
+        if (jj + 1 < j1) push(wv[u].y - pv[u].y, jj + 1);
+      }
+    }
+  } else {
+    for (int j = j0 + tid; j < j1; j += NT) push(__ldg(w + j) - ldm(s.price + j), j);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double bv = t.v1;
+    int bj = t.j1;
+    warp_argmax(bv, bj);
+    if (bj >= 0 && bj == t.j1) {
+      t.v1 = t.v2, t.j1 = t.j2;
+      t.v2 = NEG_INF, t.j2 = -1;
+    }
+    if (lane == r) {
+      s_cv[warp * 4 + r] = bv;
+      s_cj[warp * 4 + r] = bj;
+    }
+  }
+  double wb = fmax(lb, t.v1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wb = fmax(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+  if (lane == 0) s_wb[warp] = wb;
+  __syncthreads();
+  Top2 out{NEG_INF, NEG_INF, -1, -1};
+  if (warp == 0) {
+    constexpr int NCAND = NT / 32 * 4;
+    double a1 = lane < NCAND ? s_cv[lane] : NEG_INF;
+    int b1 = lane < NCAND ? s_cj[lane] : -1;
+    if (b1 < 0) a1 = NEG_INF;
+    double ev = NEG_INF;
+    int ej = -1;
+    for (int r = 0; r < kc; ++r) {
+      double bv = a1;
+      int bj = b1;
+      warp_argmax(bv, bj);
+      if (bj >= 0 && bj == b1) a1 = NEG_INF, b1 = -1;
+      if (lane == r) ev = bv, ej = bj;
+    }
+    double cb = fmax(a1, lane < NT / 32 ? s_wb[lane] : NEG_INF);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cb = fmax(cb, __shfl_xor_sync(0xffffffffu, cb, o));
+    if (lane < kc) {
+      s.lj[(int64_t)i * LIST_K + c * kc + lane] = ej >= 0 ? ej : j0 < s.m ? j0 : 0;
+      s.lw[(int64_t)i * LIST_K + c * kc + lane] = ej >= 0 ? __ldg(w + ej) : NEG_INF;
+    }
+    out.v1 = __shfl_sync(0xffffffffu, ev, 0);
+    out.j1 = __shfl_sync(0xffffffffu, ej, 0);
+    out.v2 = __shfl_sync(0xffffffffu, ev, 1);
+    out.j2 = __shfl_sync(0xffffffffu, ej, 1);
+    if (lane == 0) {
+      s_cv[0] = out.v1, s_cv[1] = out.v2, s_cv[2] = cb;
+      s_cj[0] = out.j1, s_cj[1] = out.j2;
+    }
+  }
+  __syncthreads();
+  out.v1 = s_cv[0], out.v2 = s_cv[1], out.j1 = s_cj[0], out.j2 = s_cj[1];
+  *bound_out = s_cv[2];
+  __syncthreads();
+  return out;
+}
 
 // One CHUNK [j0, j1) of a row sweep that rebuilds person i's candidate list cooperatively: nch CTAs each sweep
 // one chunk and contribute their chunk's top kc = list_k / nch objects to the list slots [c*kc, (c+1)*kc) plus a
@@ -558,7 +696,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
         const int i = ldm(&un[k]);
         bool ok = false;
         Top2 t;
-        if (ldm(&s.lvalid[i])) ok = list_bid<true>(s, i, lane, t);
+        ok = list_bid<true>(s, i, lane, t);
         if (lane == 0) {
           if (ok)
             wide_finalize_bid(s, k, i, t, eps);
@@ -572,9 +710,13 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       //      costs one memory latency instead of one CTA streaming a whole row by itself.
       const int nfail = ldm(&ctrl->nfail[parity]);
       if (gtid == 0) ctrl->nfail[parity ^ 1] = 0;
+      // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
+      // chunks at >= 1024 objects and the partial slots within their arrays
       int nch = 1;
       if (nfail > 0 && s.list_k == LIST_K) {
-        while (nch < 16 && 2 * nch * nfail <= (int)gridDim.x && s.m / (2 * nch) >= 1024) nch *= 2;
+        while (nch < 16 && nch * nfail < 2 * (int)gridDim.x && 2 * nch * nfail <= MAX_GRID_SLOTS &&
+               s.m / (2 * nch) >= 1024)
+          nch *= 2;
       }
       if (nch == 1) {
         for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
@@ -589,14 +731,15 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       } else {
         const int kc = LIST_K / nch;
         const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
-        const int items = nfail * nch;  // <= gridDim.x
+        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
           const int f = item / nch, c = item - f * nch;
           const int kk = ldm(&s.fail[f]);
           const int i = ldm(&un[kk]);
           const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
           double cb;
-          const Top2 t = chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
+          const Top2 t = kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
+                                  : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
           if (tid == 0) {
             s.pv1[item] = t.v1;
             s.pv2[item] = t.v2;
@@ -841,7 +984,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState
       const int i = s_list[cur][b];
       bool ok = false;
       Top2 t;
-      if (s.lvalid[i]) ok = list_bid<false>(s, i, lane, t);
+      ok = list_bid<false>(s, i, lane, t);
       if (lane == 0) {
         if (ok)
           finalize(b, t);
@@ -1293,19 +1436,6 @@ struct __align__(16) MhEntry {  // one list entry travelling from a helper to th
   int j, pad;
 };
 
-// warp-wide arg-max of (v, j) with the smaller index winning ties; every lane returns the winner
-__device__ __forceinline__ void warp_argmax(double& v, int& j) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, j, o);
-    if (ov > v || (ov == v && (unsigned)oj < (unsigned)j)) {
-      v = ov;
-      j = oj;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s, int mc /* objects per CTA, even */) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || !ctrl->in_tail || s.flags[0]) return;  // uniform over the cluster
@@ -1509,7 +1639,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
         const int i = s_list[cur][b];
         bool ok = false;
         Top2 t;
-        if (s.lvalid[i]) ok = list_bid<false>(s, i, lane, t);
+        ok = list_bid<false>(s, i, lane, t);
         if (lane == 0) {
           if (ok)
             finalize(b, t);
@@ -1972,7 +2102,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   const bool list_tail = use_lists != 0 && m <= list_max_m;
   // long rows: lists only pay in the rounds with at least a grid-full of bidders (failed lists are then swept by
   // whole CTAs in parallel); below that every row is split over the grid instead
-  int list_min_nu = list_tail ? 0 : (blocks > 2048 ? blocks : 2048);
+  int list_min_nu = 0;
   if ((e = getenv("MCD_LAP_LIST_MIN_NU"))) list_min_nu = atoi(e);
   int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? CL_MAX_CS : 8);
   if (cs > CL_MAX_CS) cs = CL_MAX_CS;
@@ -1991,7 +2121,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     if (cs > 8)
       MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
-  const bool mh_tail = cluster_tail && !((e = getenv("MCD_LAP_TAIL_MH")) && atoi(e) == 0);
+  // n < m: master/helper tail (candidate lists certify ~90 % of the bids).  n == m: eps-scaling flattens every
+  // person's values, ~90 % of the lists fail (measured), so the scan-every-row cluster kernel stays.
+  bool mh_tail = cluster_tail && n < m;
+  if ((e = getenv("MCD_LAP_TAIL_MH"))) mh_tail = cluster_tail && atoi(e) != 0;
   if (mh_tail && cs != 8 && cs != 16) cs = 16;
   if (mh_tail) {
     mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
