@@ -41,12 +41,15 @@ SHAPES = {  # name -> (M, N, G, clones)
 METRIC = "cell2cell_assignment wall-time"
 UNIT = "s"
 FP64_NOMINAL_TFLOPS = 40.0  # B200 datasheet FP64 (tensor) -- MEASURED_PEAKS.json carries no FP64 figure
+INT8_NOMINAL_TOPS = 4500.0  # B200 datasheet dense int8; the measured stand-in is 2 x the measured bf16 GEMM peak
 
 
 def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
     capture of `scripts/profile_pass.py C5` (profiles/r01_C5_final_ncu_summary.json).  Valid for the C5 workload."""
-    p = os.path.join(ROOT, "profiles", "r01_C5_final_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", "r01_C5_ozaki_ncu_summary.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_C5_final_ncu_summary.json")
     out = {}
     if not os.path.exists(p):
         return out
@@ -223,9 +226,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MCD_BENCH_WORKLOAD", "C5"), choices=sorted(SHAPES))
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "split"])
+    ap.add_argument("--precision", default="ozaki", choices=["ozaki", "fp64", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-split", action="store_true", help="skip the companion split-precision (tcgen05) measurement")
+    ap.add_argument("--no-split", "--no-companions", dest="no_split", action="store_true",
+                    help="skip the companion measurements of the other precision modes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -307,36 +311,47 @@ def main():
     h2d = rna_host.numel() * 8 + dna_host.numel() * 8
     d2h = M * 4 * 2 + res_e2e["objs"].size * 8
 
-    split = None
-    if world == 1 and args.precision == "fp64" and not args.no_split:
-        # companion run of the tcgen05 split-precision path on the same instance (same timing rules)
-        runner_s = mdist.ShardedCell2Cell(h, M, N, G, world, rank, device, precision="split")
-        ms_s, res_s, _ = timed(lambda: runner_s.run_device(rna_loc, dna), W, K)
-        # accuracy of its correlations against the FP64 path, whole matrix, on the device
+    companions = None
+    if world == 1 and not args.no_split:
+        # the other precision modes on the same instance (same timing rules), each compared with the FP64-pipe
+        # (DMMA) path: whole-matrix correlation error, cells assigned differently, objective gap
         lib = h.lib
-        import ctypes as C
+        nst = int(lib.mcd_num_steps(M, N))
+        cref = torch.empty((M, N), dtype=torch.float64, device=device)
+        cbuf = torch.empty((M, N), dtype=torch.float64, device=device)
+        a_ref, s_ref, a_b, s_b = (torch.empty(M, dtype=torch.int32, device=device) for _ in range(4))
+        o_ref, o_b = (torch.empty(nst, dtype=torch.float64, device=device) for _ in range(2))
 
-        c64 = torch.empty((M, N), dtype=torch.float64, device=device)
-        csp = torch.empty((M, N), dtype=torch.float64, device=device)
-        outs = [torch.empty(M, dtype=torch.int32, device=device) for _ in range(4)]
-        objs2 = [torch.empty(int(lib.mcd_num_steps(M, N)), dtype=torch.float64, device=device) for _ in range(2)]
-        for prec, cbuf, a_, s_, o_ in ((0, c64, outs[0], outs[1], objs2[0]), (1, csp, outs[2], outs[3], objs2[1])):
-            h.check(lib.mcd_cell2cell(h.h, rna_loc.data_ptr(), G, dna.data_ptr(), G, M, N, G, _lib.MEM_DEVICE, prec,
-                                      a_.data_ptr(), s_.data_ptr(), o_.data_ptr(), cbuf.data_ptr(), _lib.MEM_DEVICE,
-                                      None))
-        torch.cuda.synchronize()
-        stt = res_s["stats"]
+        def whole(prec, cb, a_, s_, o_):
+            h.check(lib.mcd_cell2cell(h.h, rna_loc.data_ptr(), G, dna.data_ptr(), G, M, N, G, _lib.MEM_DEVICE,
+                                      _lib.PREC[prec], a_.data_ptr(), s_.data_ptr(), o_.data_ptr(), cb.data_ptr(),
+                                      _lib.MEM_DEVICE, None))
+            torch.cuda.synchronize()
+
+        whole("fp64", cref, a_ref, s_ref, o_ref)
         flops_ = 2.0 * M * N * G
-        split = {
-            "value": ms_s * 1e-3, "unit": UNIT, "stage_ms": {k: stt[k] for k in ("ms_standardize", "ms_corr", "ms_lap")},
-            "corr_tflops": flops_ / (stt["ms_corr"] * 1e-3) / 1e12,
-            "tensor_tflops": 3 * flops_ / (stt["ms_corr"] * 1e-3) / 1e12,
-            "tensor_frac_of_measured_bf16": 3 * flops_ / (stt["ms_corr"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
-            "max_abs_dcorr_vs_fp64": float((c64 - csp).abs().max().item()),
-            "cells_assigned_differently_vs_fp64": int((outs[0] != outs[2]).sum().item()),
-            "rel_objective_gap_vs_fp64": float(((objs2[0] - objs2[1]).abs() / objs2[0].abs()).max().item()),
-        }
-        del c64, csp
+        nsl = int(lib.mcd_ozaki_slices_for(M, N, G))
+        mmas = {"fp64": 1, "split": 3, "ozaki": nsl * (nsl + 1) // 2}
+        tpeak = {"fp64": FP64_NOMINAL_TFLOPS, "split": peaks["bf16_tflops"], "ozaki": 2.0 * peaks["bf16_tflops"]}
+        companions = {}
+        for prec in ("ozaki", "fp64", "split"):
+            runner_c = mdist.ShardedCell2Cell(h, M, N, G, world, rank, device, precision=prec)
+            ms_c, res_c, _ = timed(lambda: runner_c.run_device(rna_loc, dna), W if prec != args.precision else 1, K)
+            stt = res_c["stats"]
+            whole(prec, cbuf, a_b, s_b, o_b)
+            tc = stt["ms_corr"] * 1e-3
+            companions[prec] = {
+                "value": ms_c * 1e-3, "unit": UNIT,
+                "stage_ms": {k: stt[k] for k in ("ms_standardize", "ms_corr", "ms_lap")},
+                "corr_tflops_fp64_equivalent": flops_ / tc / 1e12,
+                "tensor_tops": mmas[prec] * flops_ / tc / 1e12,
+                "tensor_frac": mmas[prec] * flops_ / tc / 1e12 / tpeak[prec],
+                "tensor_peak": tpeak[prec],
+                "max_abs_dcorr_vs_fp64_pipe": float((cref - cbuf).abs().max().item()),
+                "cells_assigned_differently_vs_fp64_pipe": int((a_ref != a_b).sum().item()),
+                "rel_objective_gap_vs_fp64_pipe": float(((o_ref - o_b).abs() / o_ref.abs()).max().item()),
+            }
+        del cref, cbuf
 
     if rank == 0:
         st = res_dev["stats"]
@@ -346,23 +361,29 @@ def main():
         q, r = divmod(M, N)
         assert np.bincount(res_dev["step"])[1:].tolist() == [N] * q + ([r] if r else [])
         flops = 2.0 * M * N * G
-        p_mma = 1 if args.precision == "fp64" else 3
+        nsl = int(h.lib.mcd_ozaki_slices_for(M, N, G))
+        p_mma = {"fp64": 1, "split": 3, "ozaki": nsl * (nsl + 1) // 2}[args.precision]  # tensor-core products per output
         t_corr = st["ms_corr"] * 1e-3
         t_std = st["ms_standardize"] * 1e-3
         t_lap = st["ms_lap"] * 1e-3
-        w_out = 8 if args.precision == "fp64" else 4
+        w_out = {"fp64": 8, "split": 4, "ozaki": nsl}[args.precision]  # bytes K1 writes per element
         std_bytes = (M / world + N) * G * (8 + w_out)
         lap_bytes_alg = sum(max(M - s * N, 0) and (min(M - s * N, N) * max(M - s * N, N) * 8.0) for s in range(nsteps))
-        corr_peak = FP64_NOMINAL_TFLOPS if args.precision == "fp64" else peaks["bf16_tflops"]
+        corr_peak = {"fp64": FP64_NOMINAL_TFLOPS, "split": peaks["bf16_tflops"],
+                     "ozaki": 2.0 * peaks["bf16_tflops"]}[args.precision]
+        corr_peak_source = {"fp64": "nominal B200 FP64 (no measured FP64 peak)", "split": peaks["source"] + " bf16",
+                            "ozaki": "2 x %s bf16 GEMM peak (int8 issues at twice the bf16 rate; MEASURED_PEAKS.json has "
+                                     "no int8 entry; nominal dense int8 = %.0f TOP/s)" % (peaks["source"],
+                                                                                         INT8_NOMINAL_TOPS)}[args.precision]
+        corr_kernel = {"fp64": "corr_fp64_kernel", "split": "corr_split_kernel", "ozaki": "corr_ozaki_kernel"}[args.precision]
         rooflines = {
             "standardize": {"bound": "hbm", "achieved": std_bytes / t_std / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": std_bytes / t_std / 1e9 / peaks["hbm_gbs"], "traffic": None,
                             "peak_source": peaks["source"]},
             "corr": {"bound": "tensor", "achieved": p_mma * flops / world / t_corr / 1e12, "peak": corr_peak,
                      "unit": "TFLOP/s", "frac": p_mma * flops / world / t_corr / 1e12 / corr_peak, "traffic": None,
-                     "algorithmic_tflops": flops / world / t_corr / 1e12,
-                     "peak_source": "nominal B200 FP64 (no measured FP64 peak)" if args.precision == "fp64"
-                     else peaks["source"] + " bf16"},
+                     "algorithmic_tflops": flops / world / t_corr / 1e12, "tensor_products_per_output": p_mma,
+                     "peak_source": corr_peak_source},
             "lap": {"bound": "hbm", "achieved": lap_bytes_alg / t_lap / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": lap_bytes_alg / t_lap / 1e9 / peaks["hbm_gbs"], "traffic": None,
                     "scanned_gbs": st["lap_bytes"] / t_lap / 1e9, "rounds": st["lap_rounds"], "bids": st["lap_bids"],
@@ -372,22 +393,22 @@ def main():
             tr = load_traffic()
             if "standardize_rows" in tr:  # RNA operand launch (the larger of the two)
                 rooflines["standardize"]["traffic"] = max(tr["standardize_rows"])
-            if "corr_fp64_kernel" in tr and args.precision == "fp64":
-                rooflines["corr"]["traffic"] = tr["corr_fp64_kernel"][0]
+            if corr_kernel in tr:
+                rooflines["corr"]["traffic"] = tr[corr_kernel][0]
             if "lap_auction_kernel" in tr:
                 rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
-                rooflines["lap"]["traffic_note"] = ("one wide-round launch (step 2); ncu returns no DRAM counters for "
-                                                    "the cluster kernel of the narrow rounds")
+                rooflines["lap"]["traffic_note"] = "one wide-round launch (step 1) of lap_auction_kernel"
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
-        roof["kernel"] = {"standardize": "standardize_rows", "corr": "corr_fp64_kernel" if args.precision == "fp64"
-                          else "corr_split_kernel",
-                          "lap": "lap_auction_kernel + lap_tail_cluster_kernel (assignment solver, all steps)"}[dominant]
+        roof["kernel"] = {"standardize": "standardize_rows", "corr": corr_kernel,
+                          "lap": "lap_auction_kernel + lap_tail_mh_kernel / lap_tail_cluster_kernel (assignment "
+                                 "solver, all steps)"}[dominant]
         roof["algorithmic_bytes"] = {"standardize": std_bytes, "corr": None, "lap": lap_bytes_alg}[dominant]
         line = {
             "metric": METRIC, "value": ms_dev * 1e-3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if args.precision == "fp64" else "fp16x2-split->f32", "data": "synthetic",
+            "dtype": {"fp64": "f64", "split": "fp16x2-split->f32", "ozaki": "int8-digit-slices->s32->f64"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": "%s: %d RNA x %d DNA x %d genes, %d steps" % (args.workload, M, N, G, nsteps),
                        "precision": args.precision, "l2": "inputs (%.1f GB) larger than L2" % ((M + N) * G * 8 / 1e9),
                        "parallelism": "rna-row-sharded corr x%d + allgather + replicated LAP" % world if world > 1
@@ -404,8 +425,8 @@ def main():
             "rooflines": rooflines,
             "objective": [float(x) for x in res_dev["objs"]],
         }
-        if split is not None:
-            line["split_precision"] = split
+        if companions is not None:
+            line["precision_modes"] = companions
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(M, N, G, clones)
         print(json.dumps(line))

@@ -109,6 +109,9 @@ int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t
  *   digits [nsl, ncells, ldk8] int8, ldk8 = mcd_padded_k_split(G), zero padded;  scale [ncells] = 2^-e (the
  *   factor that undoes the row scaling);  nsl in [2, 8] (mcd_ozaki_default_slices(): 6, env MCD_OZAKI_SLICES). */
 int mcd_ozaki_default_slices(void);
+/* Slice count the fused driver uses for an M x N x G instance: 8 (FP64-GEMM-level error) while M*N*G <= 2e11,
+ * 6 (~1e-12 absolute) above; MCD_OZAKI_SLICES overrides. */
+int mcd_ozaki_slices_for(int64_t M, int64_t N, int64_t G);
 int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
                           int nsl, double* scale, double* norms);
 /* Synchronise and return MCD_ERR_NONFINITE if any standardise call since the last check saw NaN/Inf. */

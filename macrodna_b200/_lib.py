@@ -74,6 +74,7 @@ SIGNATURES = {
     "mcd_standardize": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_standardize_split": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_ozaki_default_slices": (_I, []),
+    "mcd_ozaki_slices_for": (_I, [_I64, _I64, _I64]),
     "mcd_standardize_ozaki": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP, _VP]),
     "mcd_corr_ozaki": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_check_finite": (_I, [_VP]),

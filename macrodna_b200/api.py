@@ -35,7 +35,9 @@ class MaCroDNA:
     frames (index = gene ids, columns = cell ids, ``:13``); ``dna_label`` has columns
     ``clone`` and ``cell`` (``:14``).  Keyword-only extras default to reference behaviour:
 
-    * ``precision``: ``"fp64"`` (parity mode, FP64 tensor pipe) or ``"split"`` (tcgen05 fp16 hi/lo split precision);
+    * ``precision``: ``"ozaki"`` (default: FP64-equivalent correlations from the int8 tcgen05 tensor cores, exact
+      digit-slice products, ~1e-12 absolute), ``"fp64"`` (FP64 tensor pipe, DMMA) or ``"split"`` (tcgen05 fp16
+      hi/lo split precision, ~3e-7 absolute);
     * ``clone_column``: ``"predict_clone"`` (README.md:201, CRC_data_analysis/macrodna.py:195) or
       ``"predict"`` (src/MaCroDNA/macrodna.py:198);
     * ``verbose``: print the reference's progress lines (``:95-98,120,124,147``);
@@ -48,7 +50,7 @@ class MaCroDNA:
       ``predicted_dna_cell, rna_cell, step`` and no index (clonal_proportions_resampling.py:166-169).
     """
 
-    def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="fp64",
+    def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="ozaki",
                  clone_column="predict_clone", verbose=False, variant="src"):
         self._genes = None  # shared genes of the last run: the frames below are filtered lazily (see rna_df)
         self.rna_df = rna_df

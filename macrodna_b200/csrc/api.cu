@@ -148,6 +148,13 @@ int mcd_ozaki_default_slices(void) {
   return v;
 }
 
+int mcd_ozaki_slices_for(int64_t M, int64_t N, int64_t G) {
+  if (getenv("MCD_OZAKI_SLICES")) return mcd_ozaki_default_slices();
+  // 8 slices (36 products, error at the level of an FP64 GEMM's own rounding) while the contraction is cheap
+  // anyway; 6 slices (21 products, ~1e-12 absolute) once it is the large-instance bottleneck
+  return (double)M * (double)N * (double)G <= 2.0e11 ? 8 : 6;
+}
+
 int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
                           int nsl, double* scale, double* norms) {
   if (!h) return MCD_ERR_INVALID;
@@ -587,7 +594,7 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   }
   if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16 && precision != MCD_PREC_OZAKI_INT8)
     return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
-  const int nsl = mcd_ozaki_default_slices();
+  const int nsl = mcd_ozaki_slices_for(M, N, G);
   // exact int32 accumulation bounds the gene count of the integer path; longer rows use the FP64 pipe
   if (precision == MCD_PREC_OZAKI_INT8 && (double)nsl * 4096.0 * (double)mcd_padded_k_split(G) >= 2147483648.0)
     precision = MCD_PREC_FP64;

@@ -9,7 +9,7 @@ Partitioning:
   ceil(M/P) per rank so shard r lands at row r*ceil(M/P)), C^T is rebuilt locally by a
   transpose kernel, and the assignment step loop runs replicated on every rank: the solver is
   deterministic, so all ranks hold bit-identical results and no further exchange is needed.
-  (A price-exchange sharded solver is the next step; see DESIGN.md.)
+  (Why the solver is not sharded: DESIGN.md section 5.)
 * Replicate sweeps (config 4) are "replicas only": ``replicate_owner`` maps replicate -> rank,
   no collective.
 """
@@ -59,7 +59,7 @@ def gather_rows(local, M: int, world: int):
 class ShardedCell2Cell:
     """The hot path on ``world`` GPUs (world == 1: a single fused C-ABI call)."""
 
-    def __init__(self, handle, M, N, G, world, rank, device, precision="fp64"):
+    def __init__(self, handle, M, N, G, world, rank, device, precision="ozaki"):
         self.h, self.M, self.N, self.G = handle, M, N, G
         self.world, self.rank, self.device = world, rank, device
         self.precision = precision
@@ -78,18 +78,53 @@ class ShardedCell2Cell:
         if self._bufs is None:
             lib = self.h.lib
             per = -(-self.M // self.world)
-            ldk = lib.mcd_padded_k(self.G)
             ldc = (self.N + 1) & ~1
             ldct = (self.M + 1) & ~1
             f64 = dict(dtype=torch.float64, device=self.device)
+            m_loc = max(1, self.hi - self.lo)  # operand buffers hold exactly this rank's rows
+            if self.precision == "fp64":
+                ldk = lib.mcd_padded_k(self.G)
+                ops = dict(a=torch.empty((m_loc, ldk), **f64), b=torch.empty((self.N, ldk), **f64))
+            elif self.precision == "ozaki":
+                ldk = lib.mcd_padded_k_split(self.G)
+                nsl = int(lib.mcd_ozaki_slices_for(self.M, self.N, self.G))
+                i8 = dict(dtype=torch.int8, device=self.device)
+                ops = dict(a=torch.empty((nsl, m_loc, ldk), **i8), b=torch.empty((nsl, self.N, ldk), **i8),
+                           sa=torch.empty(m_loc, **f64), sb=torch.empty(self.N, **f64), nsl=nsl)
+            else:
+                ldk = lib.mcd_padded_k_split(self.G)
+                i16 = dict(dtype=torch.int16, device=self.device)
+                ops = dict(a=torch.empty((2, m_loc, ldk), **i16), b=torch.empty((2, self.N, ldk), **i16))
             self._bufs = dict(
                 per=per, ldk=ldk, ldc=ldc, ldct=ldct,
-                a=torch.empty((per, ldk), **f64), b=torch.empty((self.N, ldk), **f64),
                 na=torch.empty(per, **f64), nb=torch.empty(self.N, **f64),
                 c_loc=torch.zeros((per, ldc), **f64), ct=torch.empty((self.N, ldct), **f64),
-                rna_dev=None, dna_dev=None,
+                rna_dev=None, dna_dev=None, **ops,
             )
         return self._bufs
+
+    def _standardize_and_correlate(self, b, rna_loc, dna, m_loc, events, ext):
+        """K1 (both operands) + K2 of this rank's row block in the configured precision; C only (no C^T)."""
+        lib, h, chk = self.h.lib, self.h.h, self.h.check
+        G, N = self.G, self.N
+        pa, pb, na, nb = b["a"].data_ptr(), b["b"].data_ptr(), b["na"].data_ptr(), b["nb"].data_ptr()
+        c, ldc, ldk = b["c_loc"].data_ptr(), b["ldc"], b["ldk"]
+        if self.precision == "fp64":
+            chk(lib.mcd_standardize(h, rna_loc.data_ptr(), m_loc, G, G, pa, na))
+            chk(lib.mcd_standardize(h, dna.data_ptr(), N, G, G, pb, nb))
+            events[1].record(ext)
+            chk(lib.mcd_corr_fp64(h, pa, m_loc, pb, N, G, ldk, na, nb, c, ldc, None, 0))
+        elif self.precision == "ozaki":
+            sa, sb, nsl = b["sa"].data_ptr(), b["sb"].data_ptr(), b["nsl"]
+            chk(lib.mcd_standardize_ozaki(h, rna_loc.data_ptr(), m_loc, G, G, pa, nsl, sa, na))
+            chk(lib.mcd_standardize_ozaki(h, dna.data_ptr(), N, G, G, pb, nsl, sb, nb))
+            events[1].record(ext)
+            chk(lib.mcd_corr_ozaki(h, pa, m_loc, pb, N, G, ldk, nsl, sa, sb, na, nb, c, ldc, None, 0))
+        else:
+            chk(lib.mcd_standardize_split(h, rna_loc.data_ptr(), m_loc, G, G, pa, na))
+            chk(lib.mcd_standardize_split(h, dna.data_ptr(), N, G, G, pb, nb))
+            events[1].record(ext)
+            chk(lib.mcd_corr_split(h, pa, m_loc, pb, N, G, ldk, na, nb, c, ldc, None, 0))
 
     def _sharded(self, rna_loc, dna):
         """rna_loc: this rank's [hi-lo, G] device tensor; dna: [N, G] device tensor."""
@@ -101,14 +136,7 @@ class ShardedCell2Cell:
         m_loc = self.hi - self.lo
         e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record(ext)
-        self.h.check(lib.mcd_standardize(h, rna_loc.data_ptr(), m_loc, self.G, self.G, b["a"].data_ptr(),
-                                         b["na"].data_ptr()))
-        self.h.check(lib.mcd_standardize(h, dna.data_ptr(), self.N, self.G, self.G, b["b"].data_ptr(),
-                                         b["nb"].data_ptr()))
-        e[1].record(ext)
-        self.h.check(lib.mcd_corr_fp64(h, b["a"].data_ptr(), m_loc, b["b"].data_ptr(), self.N, self.G, b["ldk"],
-                                       b["na"].data_ptr(), b["nb"].data_ptr(), b["c_loc"].data_ptr(), b["ldc"],
-                                       None, 0))
+        self._standardize_and_correlate(b, rna_loc, dna, m_loc, e, ext)
         e[2].record(ext)
         with torch.cuda.stream(ext):
             c_full = gather_rows(b["c_loc"], self.M, self.world)
@@ -157,7 +185,7 @@ class ShardedCell2Cell:
         return out
 
 
-def sweep_assignments(handle, rna: np.ndarray, dna: np.ndarray, replicate_cols, world=1, rank=0, precision="fp64"):
+def sweep_assignments(handle, rna: np.ndarray, dna: np.ndarray, replicate_cols, world=1, rank=0, precision="ozaki"):
     """Resampling-stability sweep (config 4; reference
     ``Resampling_stability_analyses/CRC_data_analyses/clonal_proportions_resampling.py:172-201``):
     replicate r re-runs the whole hot path on ``dna[replicate_cols[r]]`` (DNA cells resampled with

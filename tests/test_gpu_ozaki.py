@@ -121,7 +121,7 @@ def test_whole_path_ozaki(handle, name):
     c_ref, a_ref, s_ref, o_ref = R.cell2cell_arrays(inst.rna, inst.dna)
     err = np.abs(corr - c_ref).max()
     print(name, "ozaki: max |dcorr| %.3g" % err)
-    assert err < 1e-10
+    assert err < 1e-13  # these instances are below the 8-slice threshold (mcd_ozaki_slices_for)
     ident, rep = tie_report(c_ref, assign, step, a_ref, s_ref, rel=1e-9)
     assert ident, rep
     assert np.abs(objs - o_ref).max() <= 1e-9 * np.abs(o_ref).max()
