@@ -251,6 +251,8 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, in front of the one JSON line
         dist.init_process_group("nccl", device_id=device)
     M, N, G, clones = SHAPES[args.workload]
     W = max(3, args.warmup)

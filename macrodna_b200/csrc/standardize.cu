@@ -62,8 +62,9 @@ __device__ __forceinline__ double group_max(double v, double* red) {
 // fixed-point integer q = rint(y * 2^(7*nsl-1)) and written as nsl balanced radix-128 digits d_t in [-64, 63],
 //   q = sum_t d_t * 128^(nsl-1-t)      (t = 0 is the most significant slice).
 // The products of two such digit vectors are exact in the tensor core's int32 accumulators.
-__device__ __forceinline__ void ozaki_digits(double y, int nsl, int d[MCD_OZAKI_MAX_SLICES]) {
-  const long long q = __double2ll_rn(scalbn(y, 7 * nsl - 1));  // |q| <= 2^(7 nsl - 2)
+// ys = y * 2^(7 nsl - 1), already scaled by the caller (one multiply by a per-row power of two).
+__device__ __forceinline__ void ozaki_digits(double ys, int nsl, int d[MCD_OZAKI_MAX_SLICES]) {
+  const long long q = __double2ll_rn(ys);  // |q| <= 2^(7 nsl - 2)
   // Adding 64 to every 7-bit field turns the balanced digits into plain bit fields: q + B = sum (d_t + 64) 128^..
   const unsigned long long B = (0x0102040810204081ull << 6) & ((1ull << (7 * nsl)) - 1ull);
   const unsigned long long qb = (unsigned long long)q + B;
@@ -159,14 +160,17 @@ standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int
     if (umax > 0.0 && isfinite(umax)) (void)frexp(umax, &ex);  // umax = f * 2^ex, f in [0.5, 1)
     const int e = -ex - 1;
     if (t == 0) oz.scale[row] = scalbn(1.0, -e);
+    // one multiplier per row: 1/nrm times the exact power of two 2^(e + 7 nsl - 1)  (bit-identical to scaling
+    // the rounded quotient afterwards: a power-of-two factor commutes with rounding)
+    const double mul = inv * scalbn(1.0, e + 7 * oz.nsl - 1);
     int8_t* o = oz.digits + row * oz.ldk8;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int g = 2 * (t + k * T);
       if (g < G) {
         int d0[MCD_OZAKI_MAX_SLICES], d1[MCD_OZAKI_MAX_SLICES];
-        ozaki_digits(scalbn(v[k].x * inv, e), oz.nsl, d0);
-        ozaki_digits((g + 1 < G) ? scalbn(v[k].y * inv, e) : 0.0, oz.nsl, d1);
+        ozaki_digits(v[k].x * mul, oz.nsl, d0);
+        ozaki_digits((g + 1 < G) ? v[k].y * mul : 0.0, oz.nsl, d1);
 #pragma unroll
         for (int sl = 0; sl < MCD_OZAKI_MAX_SLICES; ++sl)
           if (sl < oz.nsl)  // g is even and ldk8 a multiple of 64: aligned 2-byte store
@@ -258,10 +262,11 @@ standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx
     if (umax > 0.0 && isfinite(umax)) (void)frexp(umax, &ex);
     const int sh = -ex - 1;
     if (threadIdx.x == 0) oz.scale[row] = scalbn(1.0, -sh);
+    const double mul = inv1 * scalbn(1.0, sh + 7 * oz.nsl - 1);
     int8_t* o = oz.digits + row * oz.ldk8;
     for (int64_t e = threadIdx.x; e < oz.ldk8; e += 512) {
       int d[MCD_OZAKI_MAX_SLICES];
-      ozaki_digits(e < G ? scalbn((at(e) - mean) * inv1, sh) : 0.0, oz.nsl, d);
+      ozaki_digits(e < G ? (at(e) - mean) * mul : 0.0, oz.nsl, d);
 #pragma unroll
       for (int sl = 0; sl < MCD_OZAKI_MAX_SLICES; ++sl)
         if (sl < oz.nsl) o[sl * oz.slice_stride + e] = (int8_t)d[sl];
