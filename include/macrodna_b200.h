@@ -196,6 +196,35 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
  */
 int mcd_last_match_values(mcd_handle h, double* out, int64_t M, int out_space);
 
+/*
+ * Views of the RESIDENT correlation matrix -- the reference's replicate sweeps and its leave-one-out test re-run
+ * the whole class on frames that only gather or delete cells (clonal_proportions_resampling.py:177-190,
+ * run_dna_batch_removal_exp.py, run_loo_experiment.py:217-226 `np.delete(corrs, cell_idx, 0)`): the genes are
+ * untouched, so every such replicate is an index gather of the matrix the last mcd_cell2cell call left on the
+ * device.  These calls keep that matrix (and mcd_last_match_values) valid.
+ *
+ * mcd_subinstance_steps: the step loop (macrodna.py:110-145) on C[rna_rows][:, dna_cols].
+ *   rna_rows [m_sub], dna_cols [n_sub]: HOST int32 indices into the resident matrix (NULL = all, in order;
+ *   repeats allowed -- resampled replicates carry duplicate DNA cells);
+ *   assign [m_sub]: POSITION in dna_cols matched to each listed RNA row; step, step_obj as in mcd_lap_steps.
+ * mcd_corr_rows: rows of the resident matrix, out [nrows, N] row-major (the left-out cell's correlations,
+ *   run_loo_experiment.py:226).
+ */
+int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols, int64_t n_sub,
+                          int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats);
+int mcd_corr_rows(mcd_handle h, const int32_t* rows, int64_t nrows, double* out, int out_space);
+/* out[k] = C[rows[k], cols[k]] of the resident matrix (HOST indices, HOST out): the `corr_val` of a sub-instance's
+ * matched pairs (run_loo_experiment.py:285). */
+int mcd_corr_pairs(mcd_handle h, const int32_t* rows, const int32_t* cols, int64_t n, double* out);
+
+/*
+ * Random-assignment null test on the resident correlation matrix (random_assignment_test.py:233-258,
+ * random_assignment_test_median.py): `trials` independent random step-wise injective assignments; sums [trials]
+ * = sum of the matched correlations, medians [trials] = their median (NULL to skip).  Same distribution as the
+ * reference's np.random.choice chain, not the same random stream.  At most 4096 cells per side.
+ */
+int mcd_null_assignments(mcd_handle h, int64_t trials, uint64_t seed, double* sums, double* medians, int out_space);
+
 /* Number of steps ceil(M/N) (macrodna.py:118-123). */
 int64_t mcd_num_steps(int64_t M, int64_t N);
 

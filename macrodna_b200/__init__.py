@@ -4,7 +4,7 @@
 import line, README.md:73) gives the drop-in class; the numeric work lives in
 ``libmacrodna_b200.so`` (``include/macrodna_b200.h``).
 """
-from .api import MaCroDNA, get_handle  # noqa: F401
+from .api import MaCroDNA, get_handle, random_test  # noqa: F401
 
-__all__ = ["MaCroDNA", "get_handle"]
+__all__ = ["MaCroDNA", "get_handle", "random_test"]
 __version__ = "0.1.0"

@@ -83,6 +83,10 @@ SIGNATURES = {
     "mcd_transpose_f64": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I64]),
     "mcd_last_match_values": (_I, [_VP, _VP, _I64, _I]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_subinstance_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
+    "mcd_corr_rows": (_I, [_VP, _VP, _I64, _VP, _I]),
+    "mcd_corr_pairs": (_I, [_VP, _VP, _VP, _I64, _VP]),
+    "mcd_null_assignments": (_I, [_VP, _I64, C.c_uint64, _VP, _VP, _I]),
     "mcd_lap_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
     "mcd_cell2cell_gather": (
         _I,
@@ -147,6 +151,7 @@ class Handle:
             )
         self.h = h
         self.device = device
+        self.resident_token = None  # identifies the run whose correlation matrix is resident (api.MaCroDNA)
 
     def close(self):
         if getattr(self, "h", None):
@@ -180,6 +185,7 @@ class Handle:
         """``rna``/``dna``: numpy arrays (host) or integer device pointers; cells x genes float64.
         ``rna_gene_idx`` / ``dna_gene_idx``: optional int32 arrays [G] -- column of each shared gene in the
         operand's block (the gene intersection is then gathered on the device)."""
+        self.resident_token = None  # whoever relied on the previous resident correlation matrix must recompute
         nsteps = self.lib.mcd_num_steps(M, N)
         if assign is None:
             assign = np.empty(M, dtype=np.int32)
@@ -206,7 +212,50 @@ class Handle:
         self.check(self.lib.mcd_last_match_values(self.h, _ptr(out), M, MEM_HOST))
         return out
 
+    # ---- views of the correlation matrix the last cell2cell call left resident ----------------------
+    def subinstance(self, rna_rows=None, dna_cols=None, M=None, N=None):
+        """Step loop on C[rna_rows][:, dna_cols] (None = all).  Returns (assign, step, objs, stats); ``assign``
+        holds POSITIONS in ``dna_cols``."""
+        if rna_rows is not None:
+            rna_rows = np.ascontiguousarray(rna_rows, dtype=np.int32)
+            m = rna_rows.size
+        else:
+            m = int(M)
+        if dna_cols is not None:
+            dna_cols = np.ascontiguousarray(dna_cols, dtype=np.int32)
+            n = dna_cols.size
+        else:
+            n = int(N)
+        nsteps = self.lib.mcd_num_steps(m, n)
+        assign = np.empty(m, dtype=np.int32)
+        step = np.empty(m, dtype=np.int32)
+        objs = np.empty(nsteps, dtype=np.float64)
+        stats = McdStats()
+        self.check(self.lib.mcd_subinstance_steps(self.h, _ptr(rna_rows), m, _ptr(dna_cols), n, _ptr(assign), _ptr(step),
+                                                  _ptr(objs), MEM_HOST, C.byref(stats)))
+        return assign, step, objs, stats
+
+    def corr_rows(self, rows, N):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.empty((rows.size, int(N)), dtype=np.float64)
+        self.check(self.lib.mcd_corr_rows(self.h, _ptr(rows), rows.size, _ptr(out), MEM_HOST))
+        return out
+
+    def corr_pairs(self, rows, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.empty(rows.size, dtype=np.float64)
+        self.check(self.lib.mcd_corr_pairs(self.h, _ptr(rows), _ptr(cols), rows.size, _ptr(out)))
+        return out
+
+    def null_assignments(self, trials, seed=2023, medians=False):
+        sums = np.empty(int(trials), dtype=np.float64)
+        med = np.empty(int(trials), dtype=np.float64) if medians else None
+        self.check(self.lib.mcd_null_assignments(self.h, int(trials), int(seed), _ptr(sums), _ptr(med), MEM_HOST))
+        return (sums, med) if medians else sums
+
     def lap_steps(self, C_ptr, ldc, Ct_ptr, ldct, M, N, out_space=MEM_HOST, assign=None, step=None, step_obj=None):
+        self.resident_token = None
         nsteps = self.lib.mcd_num_steps(M, N)
         if assign is None:
             assign = np.empty(M, dtype=np.int32)

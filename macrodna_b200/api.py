@@ -162,6 +162,10 @@ class MaCroDNA:
             raise ValueError("unassigned RNA cell")  # list.index(1), macrodna.py:160
         self.last_assign, self.last_step, self.last_objective = assign, step, objs
         self.last_stats = stats.as_dict()
+        # the correlation matrix of THIS run stays on the device until the handle's next cell2cell call
+        h.resident_token = self._resident_token = object()
+        self._resident_shape = (M, N)
+        self._resident_cells = (rna_cells, dna_cells)
         self.last_corr_val = h.last_match_values(M) if self.keep_corr_val else None
         if self.verbose:
             for o in objs:
@@ -193,6 +197,84 @@ class MaCroDNA:
             return (tmp_result, tmp_result_tagged, float(np.sum(self.last_objective)),
                     float(np.median(self.last_corr_val)))
         return tmp_result, tmp_result_tagged
+
+    # -- views of the resident correlation matrix (replicate sweeps, leave-one-out) -----------------
+    def _ensure_resident(self):
+        h = get_handle(self.device)
+        if getattr(self, "_resident_token", None) is None or getattr(h, "resident_token", None) is not self._resident_token:
+            self._run()  # the reference recomputes `corrs` on every call anyway (run_loo_experiment.py:217-221)
+        return h
+
+    def subinstance_assignment(self, rna_cells=None, dna_cells=None):
+        """Re-run the step loop on a replicate that only gathers cells of the frames of the last run: ``dna_cells``
+        may repeat and drop DNA cell ids (``new_dna = dna.loc[:, names]``, clonal_proportions_resampling.py:184-190;
+        run_dna_batch_removal_exp.py), ``rna_cells`` selects RNA cells.  The correlation matrix is NOT recomputed
+        (genes are untouched: the replicate's matrix is an index gather of the resident one).  Returns the
+        ``"resampling"`` frame ``[predicted_dna_cell, rna_cell, step]`` (clonal_proportions_resampling.py:166-169)."""
+        h = self._ensure_resident()
+        all_rna, all_dna = self._resident_cells
+        M, N = self._resident_shape
+        rows = cols = None
+        sel_rna, sel_dna = all_rna, all_dna
+        if rna_cells is not None:
+            pos = {c: k for k, c in enumerate(all_rna)}
+            sel_rna = list(rna_cells)
+            if len(set(sel_rna)) != len(sel_rna):
+                raise ValueError("duplicate RNA cell ids")
+            rows = np.array([pos[c] for c in sel_rna], dtype=np.int32)
+        if dna_cells is not None:
+            pos = {}
+            for k, c in enumerate(all_dna):
+                pos.setdefault(c, k)
+            sel_dna = list(dna_cells)
+            cols = np.array([pos[c] for c in sel_dna], dtype=np.int32)
+        assign, step, objs, stats = h.subinstance(rows, cols, M=M, N=N)
+        self.last_sub = {"assign": assign, "step": step, "objs": objs, "stats": stats.as_dict()}
+        pred = [sel_dna[j] for j in assign.tolist()]
+        return pd.DataFrame(list(zip(pred, sel_rna, step.tolist())), columns=["predicted_dna_cell", "rna_cell", "step"])
+
+    def leave_one_out(self, cell_idx, K_steps, biopsy_name=None):
+        """run_loo_experiment.py:201-319.  The RNA cell at position ``cell_idx`` is removed, the step loop runs on the
+        remaining cells (``np.delete(corrs, cell_idx, 0)``, :224), and the left-out cell takes the DNA cell of
+        highest correlation that has at most ``K_steps - 1`` matches (:298-309).  Returns
+        ``(frame[predicted_dna_cell, step, corr_val] indexed by rna_cell, sum of the objective values)``; the left-out
+        cell's row carries ``step == "TEST"``."""
+        h = self._ensure_resident()
+        rna_cells, dna_cells = self._resident_cells
+        M, N = self._resident_shape
+        if not 0 <= cell_idx < M:
+            raise IndexError("pop index out of range")  # rna_cells.pop(cell_idx), :206
+        rows = np.delete(np.arange(M, dtype=np.int32), cell_idx)
+        rest = [c for k, c in enumerate(rna_cells) if k != cell_idx]
+        obj_scores = []
+        if rows.size:
+            assign, step, objs, _ = h.subinstance(rows, None, M=M, N=N)
+            vals = h.corr_pairs(rows, assign)
+            obj_scores = [float(o) for o in objs]
+        else:
+            assign = np.empty(0, dtype=np.int32)
+            step = np.empty(0, dtype=np.int32)
+            vals = np.empty(0)
+        res_dna = [dna_cells[j] for j in assign.tolist()]
+        res_rna = list(rest)
+        res_tag = step.tolist()
+        res_val = vals.tolist()
+        cell_corr = h.corr_rows([cell_idx], N)[0]                     # np.take(corrs, cell_idx, axis=0), :226
+        cnt = np.bincount(assign, minlength=N)                       # np.count_nonzero(tagged, axis=0), :296
+        eligible = cnt <= (K_steps - 1)                              # :298
+        for idx_ in np.argsort(cell_corr)[::-1]:                     # :300-309
+            if eligible[idx_]:
+                res_dna.append(dna_cells[idx_])
+                res_rna.append(rna_cells[cell_idx])
+                res_tag.append("TEST")
+                obj_scores.append(float(cell_corr[idx_]))
+                res_val.append(float(cell_corr[idx_]))
+                break
+        tagged = pd.DataFrame(list(zip(res_dna, res_rna, res_tag, res_val)),
+                              columns=["predicted_dna_cell", "rna_cell", "step", "corr_val"]).set_index("rna_cell")
+        if self.verbose:
+            print("name of the left-out RNA cell %s from sample %s" % (rna_cells[cell_idx], biopsy_name))
+        return tagged, float(sum(obj_scores))
 
     def cell2clone_assignment(self):
         """macrodna.py:188-199: cell2cell + ``dna_label.set_index("cell").loc[predict_cell]["clone"]``."""
@@ -230,3 +312,34 @@ class MaCroDNA:
         print("Test Success")
         print("**********")
         return out
+
+
+class random_test:
+    """Mirror of ``random_test`` (Resampling_stability_analyses/BE_data_analyses/random_assignment_test.py:198-258):
+    random step-wise injective assignments over the correlation matrix, as the null distribution of the objective.
+    The matrix is computed once on the device (the constructor runs the hot path); ``assign()`` returns the sum of
+    the matched correlations of ONE random assignment like the reference, drawn from batches generated by
+    ``mcd_null_assignments``; ``assign_many`` returns a whole batch (optionally with the medians of
+    random_assignment_test_median.py).  Same distribution as the reference, not NumPy's random stream."""
+
+    def __init__(self, rna_df=None, dna_df=None, *, device=0, precision="ozaki", seed=2023, batch=4096):
+        self._m = MaCroDNA(rna_df, dna_df, device=device, precision=precision)
+        self._m._run()
+        self.dna_cells, self.rna_cells = list(self._m._resident_cells[1]), list(self._m._resident_cells[0])
+        M, N = self._m._resident_shape
+        self.quotient, self.remainder = divmod(M, N)
+        self.n_iters = self.quotient + (1 if self.remainder else 0)
+        self._seed, self._batch, self._buf, self._pos, self._draws = int(seed), int(batch), None, 0, 0
+
+    def assign_many(self, trials, seed=None, medians=False):
+        h = self._m._ensure_resident()
+        return h.null_assignments(trials, self._seed if seed is None else seed, medians=medians)
+
+    def assign(self):
+        if self._buf is None or self._pos >= len(self._buf):
+            self._buf = self.assign_many(self._batch, seed=self._seed + 7919 * self._draws)
+            self._draws += 1
+            self._pos = 0
+        v = float(self._buf[self._pos])
+        self._pos += 1
+        return v

@@ -340,6 +340,31 @@ __global__ void gather_match_kernel(const double* __restrict__ C, int64_t ldc, c
   }
 }
 
+// sub[i, j] = C[rows[i], cols[j]]  (rows / cols may repeat: resampled replicates carry duplicate DNA cells)
+__global__ void gather_sub_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
+                                  const int* __restrict__ cols, int64_t m, int64_t n, double* __restrict__ sub,
+                                  int64_t lds) {
+  const int64_t i = blockIdx.y;
+  const double* src = C + (int64_t)(rows ? rows[i] : i) * ldc;
+  double* dst = sub + i * lds;
+  for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    dst[j] = src[cols ? cols[j] : j];
+}
+
+__global__ void gather_rows_out_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
+                                       int64_t n, double* __restrict__ out) {
+  const int64_t i = blockIdx.y;
+  const double* src = C + (int64_t)rows[i] * ldc;
+  for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    out[i * n + j] = src[j];
+}
+
+__global__ void gather_pairs_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
+                                    const int* __restrict__ cols, int64_t n, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = C[(int64_t)rows[k] * ldc + cols[k]];
+}
+
 cudaEvent_t get_event(mcd_context* h, size_t idx) {
   while (h->ev.size() <= idx) {
     cudaEvent_t e;
@@ -832,6 +857,164 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   h->last_N = N;
   h->last_ldc = ldc;
   h->last_assign = d_assign;
+  return MCD_OK;
+}
+
+int mcd_corr_rows(mcd_handle h, const int32_t* rows, int64_t nrows, double* out, int out_space) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!rows || !out || nrows < 1 || h->last_M < 1 || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_rows: no mcd_cell2cell result is resident");
+  for (int64_t i = 0; i < nrows; ++i)
+    if (rows[i] < 0 || rows[i] >= h->last_M) return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_rows: row out of range");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  const int64_t N = h->last_N;
+  void* pi = nullptr;
+  void* po = nullptr;
+  int st;
+  if ((st = mcd_ws(h, WS_SUB_IDX, (size_t)nrows * 4, &pi))) return st;
+  MCD_CUDA(h, cudaMemcpyAsync(pi, rows, (size_t)nrows * 4, cudaMemcpyHostToDevice, h->stream));
+  double* dst = out;
+  if (out_space != MCD_MEM_DEVICE) {
+    if ((st = mcd_ws(h, WS_SUB_C, (size_t)nrows * N * 8, &po))) return st;
+    dst = static_cast<double*>(po);
+  }
+  dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), (unsigned)nrows);
+  gather_rows_out_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const double*>(h->ws[WS_C].ptr), h->last_ldc,
+                                                      static_cast<const int*>(pi), N, dst);
+  MCD_LAUNCH_CHECK(h, "gather_rows_out_kernel");
+  if (out_space != MCD_MEM_DEVICE)
+    MCD_CUDA(h, cudaMemcpyAsync(out, dst, (size_t)nrows * N * 8, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MCD_OK;
+}
+
+int mcd_corr_pairs(mcd_handle h, const int32_t* rows, const int32_t* cols, int64_t n, double* out) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!rows || !cols || !out || n < 1 || h->last_M < 1 || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_pairs: no mcd_cell2cell result is resident");
+  for (int64_t k = 0; k < n; ++k)
+    if (rows[k] < 0 || rows[k] >= h->last_M || cols[k] < 0 || cols[k] >= h->last_N)
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_corr_pairs: index out of range");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  void* pi = nullptr;
+  void* po = nullptr;
+  int st;
+  if ((st = mcd_ws(h, WS_SUB_IDX, (size_t)n * 8, &pi))) return st;
+  if ((st = mcd_ws(h, WS_SUB_MISC, (size_t)n * 8, &po))) return st;
+  int* d_r = static_cast<int*>(pi);
+  int* d_c = d_r + n;
+  MCD_CUDA(h, cudaMemcpyAsync(d_r, rows, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(d_c, cols, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  gather_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(static_cast<const double*>(h->ws[WS_C].ptr),
+                                                                        h->last_ldc, d_r, d_c, n,
+                                                                        static_cast<double*>(po));
+  MCD_LAUNCH_CHECK(h, "gather_pairs_kernel");
+  MCD_CUDA(h, cudaMemcpyAsync(out, po, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MCD_OK;
+}
+
+int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols, int64_t n_sub,
+                          int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!assign || !step || m_sub < 1 || n_sub < 1 || h->last_M < 1 || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_steps: no mcd_cell2cell result is resident");
+  if ((!rna_rows && m_sub != h->last_M) || (!dna_cols && n_sub != h->last_N))
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_steps: NULL index means all rows / columns");
+  for (int64_t i = 0; rna_rows && i < m_sub; ++i)
+    if (rna_rows[i] < 0 || rna_rows[i] >= h->last_M)
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_steps: RNA row out of range");
+  for (int64_t j = 0; dna_cols && j < n_sub; ++j)
+    if (dna_cols[j] < 0 || dna_cols[j] >= h->last_N)
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_steps: DNA column out of range");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  int st;
+  const int64_t lds = (n_sub + 1) & ~1LL, ldst = (m_sub + 1) & ~1LL;
+  void *pc = nullptr, *pct = nullptr, *pi = nullptr, *misc = nullptr;
+  if ((st = mcd_ws(h, WS_SUB_C, (size_t)m_sub * lds * 8, &pc))) return st;
+  if ((st = mcd_ws(h, WS_SUB_CT, (size_t)n_sub * ldst * 8, &pct))) return st;
+  if ((st = mcd_ws(h, WS_SUB_IDX, (size_t)(m_sub + n_sub) * 4, &pi))) return st;
+  int* d_rows = rna_rows ? static_cast<int*>(pi) : nullptr;
+  int* d_cols = dna_cols ? static_cast<int*>(pi) + m_sub : nullptr;
+  if (rna_rows) MCD_CUDA(h, cudaMemcpyAsync(d_rows, rna_rows, (size_t)m_sub * 4, cudaMemcpyHostToDevice, h->stream));
+  if (dna_cols) MCD_CUDA(h, cudaMemcpyAsync(d_cols, dna_cols, (size_t)n_sub * 4, cudaMemcpyHostToDevice, h->stream));
+  const int64_t launches0 = h->launches;
+  const size_t EV_LAP = 8;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
+  double* subC = static_cast<double*>(pc);
+  double* subCt = static_cast<double*>(pct);
+  {
+    dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), (unsigned)m_sub);
+    gather_sub_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const double*>(h->ws[WS_C].ptr), h->last_ldc, d_rows,
+                                                   d_cols, m_sub, n_sub, subC, lds);
+    MCD_LAUNCH_CHECK(h, "gather_sub_kernel");
+  }
+  if ((st = mcd_transpose_f64(h, subC, m_sub, n_sub, lds, subCt, ldst))) return st;
+  const int64_t nsteps = mcd_num_steps(m_sub, n_sub);
+  const size_t mi = ((size_t)m_sub * 4 + 255) / 256 * 256;
+  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
+  if ((st = mcd_ws(h, WS_SUB_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc))) return st;
+  char* mb = static_cast<char*>(misc);
+  int* d_assign = reinterpret_cast<int*>(mb);
+  int* d_step = reinterpret_cast<int*>(mb + mi);
+  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
+  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
+  if ((st = enqueue_step_loop(h, subC, lds, subCt, ldst, m_sub, n_sub, d_assign, d_step, d_obj, d_cnt, EV_LAP, false)))
+    return st;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
+  const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)m_sub * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)m_sub * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  int bad = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  for (int64_t s = 0; s < nsteps; ++s) {
+    if (hc[s].status) bad = 1;
+    if (stats) {
+      stats->lap_rounds += hc[s].rounds;
+      stats->lap_bids += hc[s].bids;
+      stats->lap_bytes += hc[s].bytes;
+      stats->lap_aug_rows += hc[s].aug_rows;
+      stats->lap_aug_steps += hc[s].aug_steps;
+    }
+  }
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
+    stats->ms_lap = ms;
+    stats->ms_total = ms;
+    stats->n_steps = nsteps;
+    stats->kernel_launches = h->launches - launches0;
+  }
+  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  return MCD_OK;
+}
+
+int mcd_null_assignments(mcd_handle h, int64_t trials, uint64_t seed, double* sums, double* medians, int out_space) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!sums || trials < 1 || h->last_M < 1 || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_null_assignments: no mcd_cell2cell result is resident");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  double* d_s = sums;
+  double* d_m = medians;
+  int st;
+  if (out_space != MCD_MEM_DEVICE) {
+    void* p = nullptr;
+    if ((st = mcd_ws(h, WS_SUB_MISC, (size_t)trials * 16, &p))) return st;
+    d_s = static_cast<double*>(p);
+    d_m = medians ? d_s + trials : nullptr;
+  }
+  if ((st = mcd_launch_null_assignments(h, static_cast<const double*>(h->ws[WS_C].ptr), h->last_ldc, h->last_M,
+                                        h->last_N, trials, seed, d_s, d_m)))
+    return st;
+  if (out_space != MCD_MEM_DEVICE) {
+    MCD_CUDA(h, cudaMemcpyAsync(sums, d_s, (size_t)trials * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (medians) MCD_CUDA(h, cudaMemcpyAsync(medians, d_m, (size_t)trials * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
   return MCD_OK;
 }
 

@@ -22,7 +22,7 @@ struct mcd_context {
   int* d_flags = nullptr;  // [0] non-finite input seen, [1..] spare
   int64_t launches = 0;
   // grow-only device workspace slots (reused across calls)
-  mcd_buffer ws[20];
+  mcd_buffer ws[24];
   // pinned host staging
   void* h_stage[2] = {nullptr, nullptr};
   size_t h_stage_bytes = 0;
@@ -50,6 +50,10 @@ enum {
   WS_MISC,
   WS_GIDX,  // gene gather indices (rna, dna)
   WS_SCALE, // Ozaki row scales (rna then dna)
+  WS_SUB_C,    // sub-instance views of the resident correlation matrix (replicate sweeps / leave-one-out)
+  WS_SUB_CT,
+  WS_SUB_IDX,
+  WS_SUB_MISC,
 };
 
 int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);
@@ -95,6 +99,10 @@ int mcd_launch_corr_fp64(mcd_context* h, const double* A, int64_t M, const doubl
 int mcd_launch_corr_split(mcd_context* h, const uint16_t* A_hi, const uint16_t* A_lo, int64_t M,
                           const uint16_t* B_hi, const uint16_t* B_lo, int64_t N, int64_t ldk16, const double* nA,
                           const double* nB, double* C, int64_t ldc, double* Ct, int64_t ldct);
+
+// Random-assignment null test on a resident correlation matrix (null_test.cu).
+int mcd_launch_null_assignments(mcd_context* h, const double* C, int64_t ldc, int64_t M, int64_t N, int64_t trials,
+                                uint64_t seed, double* d_sums, double* d_medians);
 
 struct mcd_lap_counters {  // device-resident, one per solve
   long long rounds;

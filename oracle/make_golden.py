@@ -112,6 +112,37 @@ def make_reference_cases():
     print("reference cases:", [c["name"] for c in cases])
 
 
+def make_loo_cases():
+    """Leave-one-out fixtures from the reference's own class (run_loo_experiment.py, byte-unmodified, shimmed)."""
+    import contextlib
+    import io
+
+    mod = RR.load_reference_module("loo")
+    rng = np.random.default_rng(4711)
+    cases = []
+    for name, (m, n, g) in (("loo_m9_n4", (9, 4, 30)), ("loo_m6_n7", (6, 7, 24)), ("loo_m12_n4", (12, 4, 40))):
+        genes = ["g%03d" % i for i in range(g)]
+        rna = pd.DataFrame(np.log1p(rng.poisson(3.0, (g, m)).astype(float)), index=genes, columns=["r%02d" % i for i in range(m)])
+        dna = pd.DataFrame(np.log1p(rng.integers(1, 5, (g, n)) * (1 + 0.05 * rng.standard_normal((g, n)))), index=genes,
+                           columns=["d%02d" % i for i in range(n)])
+        with RR._pandas_set_indexer_patch(), contextlib.redirect_stdout(io.StringIO()):
+            obj = mod.MaCroDNA(rna.copy(), dna.copy())
+            _, tagged, total, k = obj.cell2cell_assignment()
+            runs = []
+            for q in range(m):
+                t, s_ = obj.leave_one_out(cell_idx=q, K_steps=k, biopsy_name=name)
+                runs.append({"rna_cell": list(t.index), "predicted_dna_cell": t["predicted_dna_cell"].tolist(),
+                             "step": [x if isinstance(x, str) else int(x) for x in t["step"].tolist()],
+                             "corr_val": [float(x) for x in t["corr_val"].tolist()], "objective": float(s_)})
+        cases.append({"name": name, "genes": genes, "rna_cells": list(rna.columns), "dna_cells": list(dna.columns),
+                      "rna": rna.to_numpy().tolist(), "dna": dna.to_numpy().tolist(), "K": int(k),
+                      "full_objective": float(total), "full_corr_val": [float(x) for x in tagged["corr_val"].tolist()],
+                      "loo": runs})
+    with open(os.path.join(GOLDEN, "loo_cases.json"), "w") as f:
+        json.dump({"generator": "oracle/make_golden.py::make_loo_cases", "cases": cases}, f)
+    print("loo cases:", [c["name"] for c in cases])
+
+
 def make_synth(names=("C2", "C3", "C4")):
     for name in names:
         inst = synth.make_config_arrays(name)
@@ -139,6 +170,7 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     if RR.reference_available():
         make_reference_cases()
+        make_loo_cases()
     else:
         print("reference not available: skipping reference_cases.json")
     make_synth()

@@ -119,6 +119,49 @@ def step_loop(corrs: np.ndarray):
     return assign, step, np.asarray(objs, dtype=np.float64)
 
 
+def leave_one_out(corrs: np.ndarray, cell_idx: int, k_steps: int):
+    """``leave_one_out`` of Resampling_stability_analyses/BE_data_analyses/run_loo_experiment.py:201-319 on a
+    given correlation matrix: delete row ``cell_idx`` (:224), run the step loop on the rest (:246-269), then give
+    the left-out cell the DNA cell of highest correlation among those with at most ``k_steps - 1`` matches
+    (:296-309).  Returns (assign_rest, step_rest, objs_rest, test_dna or -1, test_corr, total objective)."""
+    loo = np.delete(corrs, cell_idx, 0)
+    if loo.shape[0]:
+        assign, step, objs = step_loop(loo)
+    else:
+        assign, step, objs = np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0)
+    cell = corrs[cell_idx]
+    cnt = np.bincount(assign, minlength=corrs.shape[1])
+    test_dna, test_val = -1, 0.0
+    for idx_ in np.argsort(cell)[::-1]:
+        if cnt[idx_] <= k_steps - 1:
+            test_dna, test_val = int(idx_), float(cell[idx_])
+            break
+    total = float(np.sum(objs)) + (test_val if test_dna >= 0 else 0.0)
+    return assign, step, objs, test_dna, test_val, total
+
+
+def random_assign(corrs: np.ndarray, rng) -> float:
+    """One draw of ``random_test.assign`` (random_assignment_test.py:233-258) with ``rng.choice`` in place of
+    ``np.random.choice``: per step a random N-subset of the remaining RNA rows against all DNA columns, the last
+    (short) step a random injective map of the remaining rows into the DNA columns; returns the sum."""
+    n_rna, n_dna = corrs.shape
+    rna_idx = np.arange(n_rna)
+    dna_idx = np.arange(n_dna)
+    s = 0.0
+    removed = []
+    for _ in range(n_steps(n_rna, n_dna)):
+        n_min = min(len(rna_idx), len(dna_idx))
+        if n_min == len(rna_idx):
+            sel = rng.choice(dna_idx, n_min, replace=False)
+            s += corrs[rna_idx, sel].sum()
+        else:
+            sel = rng.choice(rna_idx, n_min, replace=False)
+            s += corrs[sel, dna_idx].sum()
+            removed.append(sel)
+            rna_idx = np.delete(np.arange(n_rna), np.concatenate(removed))
+    return float(s)
+
+
 def cell2cell_arrays(rna_np: np.ndarray, dna_np: np.ndarray):
     """Array-level restatement: cells x genes float64 in, (corrs, assign, step, objs) out."""
     corrs = correlation_matrix(rna_np, dna_np)

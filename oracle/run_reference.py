@@ -27,6 +27,8 @@ _SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
 VARIANTS = {
     "src": "src/MaCroDNA/macrodna.py",
     "crc": "CRC_data_analysis/macrodna.py",
+    "loo": "Resampling_stability_analyses/BE_data_analyses/run_loo_experiment.py",
+    "random": "Resampling_stability_analyses/BE_data_analyses/random_assignment_test.py",
 }
 
 
@@ -52,6 +54,21 @@ def _pandas_set_indexer_patch():
         yield
     finally:
         indexing._LocIndexer.__getitem__ = orig
+
+
+def load_reference_module(variant: str = "src"):
+    """Import a reference file as a module (its ``__main__`` block does not run), with the shim on the path."""
+    path = os.path.join(REFERENCE_ROOT, VARIANTS[variant])
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
+    sys.path.insert(0, _SHIM_DIR)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_module_" + variant, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(_SHIM_DIR)
+    return mod
 
 
 def load_reference_class(variant: str = "src"):

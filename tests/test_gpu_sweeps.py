@@ -1,0 +1,92 @@
+"""GPU tests of the views on the resident correlation matrix: replicate sub-instances, leave-one-out, null test."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, tie_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(rng, m, n, g):
+    genes = ["g%03d" % i for i in range(g)]
+    rna = pd.DataFrame(np.log1p(rng.poisson(3.0, (g, m)).astype(float)), index=genes, columns=["r%03d" % i for i in range(m)])
+    dna = pd.DataFrame(np.log1p(rng.integers(1, 5, (g, n)) * (1 + 0.05 * rng.standard_normal((g, n)))), index=genes,
+                       columns=["d%03d" % i for i in range(n)])
+    return rna, dna
+
+
+def test_subinstance_resampled_dna_and_dropped_cells(handle):
+    """A replicate with duplicated / dropped DNA cells and a subset of RNA cells equals a from-scratch run on the
+    gathered frames (clonal_proportions_resampling.py:184-190) and the oracle on the gathered matrix."""
+    from macrodna_b200 import MaCroDNA
+    from oracle import restatement as R
+
+    rng = np.random.default_rng(8)
+    rna, dna = _frames(rng, 57, 13, 200)
+    m = MaCroDNA(rna.copy(), dna.copy(), variant="resampling")
+    base = m.cell2cell_assignment()
+    names = list(rng.choice(dna.columns, size=9, replace=True))
+    keep_rna = [c for k, c in enumerate(rna.columns) if k % 5 != 2]
+    sub = m.subinstance_assignment(rna_cells=keep_rna, dna_cells=names)
+    corrs = R.correlation_matrix(rna.T.to_numpy(), dna.T.to_numpy())
+    rows = [list(rna.columns).index(c) for c in keep_rna]
+    cols = [list(dna.columns).index(c) for c in names]
+    a_ref, s_ref, o_ref = R.step_loop(corrs[np.ix_(rows, cols)])
+    assert np.allclose(m.last_sub["objs"], o_ref, rtol=1e-12, atol=1e-13)
+    ident, rep = tie_report(corrs[np.ix_(rows, cols)], m.last_sub["assign"], m.last_sub["step"], a_ref, s_ref, 1e-12)
+    assert rep["objective_ok"], rep  # duplicated DNA columns are exact ties: objectives must agree step by step
+    assert sub["rna_cell"].tolist() == keep_rna and set(sub["predicted_dna_cell"]) <= set(names)
+    # the resident matrix survived: the base run is still what the handle answers for
+    again = m.subinstance_assignment()
+    assert again.equals(base)
+    fresh = MaCroDNA(rna[keep_rna].copy(), dna.loc[:, names].copy(), variant="objective").cell2cell_assignment()
+    assert abs(fresh[2] - o_ref.sum()) <= 1e-12 * abs(o_ref.sum())
+
+
+def test_leave_one_out_matches_reference_fixtures(handle):
+    from macrodna_b200 import MaCroDNA
+
+    with open(os.path.join(GOLDEN, "loo_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    for case in cases:
+        rna = pd.DataFrame(np.asarray(case["rna"]), index=case["genes"], columns=case["rna_cells"])
+        dna = pd.DataFrame(np.asarray(case["dna"]), index=case["genes"], columns=case["dna_cells"])
+        m = MaCroDNA(rna, dna, variant="loo")
+        _, tagged, total, k = m.cell2cell_assignment()
+        assert k == case["K"] and abs(total - case["full_objective"]) < 1e-11
+        for q, ref in enumerate(case["loo"]):
+            t, s = m.leave_one_out(cell_idx=q, K_steps=k, biopsy_name=case["name"])
+            assert list(t.index) == ref["rna_cell"]
+            assert t["predicted_dna_cell"].tolist() == ref["predicted_dna_cell"]
+            assert t["step"].tolist() == ref["step"]
+            assert np.allclose(t["corr_val"].to_numpy(dtype=float), ref["corr_val"], rtol=0, atol=1e-11)
+            assert abs(s - ref["objective"]) < 1e-11
+
+
+@pytest.mark.parametrize("mn", [(11, 4), (6, 9), (40, 40), (230, 57)])
+def test_null_assignments_distribution(handle, mn):
+    """Every RNA cell meets a uniformly random DNA cell, injectively within a step: the mean of the statistic is
+    exactly sum_i mean_j C[i, j]; the spread must match the oracle's draw-by-draw restatement of the reference."""
+    from macrodna_b200 import random_test
+    from oracle import restatement as R
+
+    M, N = mn
+    rng = np.random.default_rng(M + N)
+    rna, dna = _frames(rng, M, N, 150)
+    rt = random_test(rna, dna)
+    assert rt.n_iters == R.n_steps(M, N)
+    sums, med = rt.assign_many(20000, seed=5, medians=True)
+    corrs = R.correlation_matrix(rna.T.to_numpy(), dna.T.to_numpy())
+    expect = corrs.mean(axis=1).sum()
+    assert abs(sums.mean() - expect) < 4.5 * sums.std() / np.sqrt(len(sums))
+    ref = np.array([R.random_assign(corrs, rng) for _ in range(4000)])
+    assert abs(sums.std() - ref.std()) < 0.08 * ref.std()
+    assert np.quantile(sums, 0.999) <= R.step_loop(corrs)[2].sum() + 1e-9  # nothing beats the optimum
+    assert (med >= corrs.min() - 1e-12).all() and (med <= corrs.max() + 1e-12).all()
+    again = rt.assign_many(20000, seed=5)
+    assert (again == sums).all()  # deterministic in (seed, trial)
+    assert isinstance(rt.assign(), float)
