@@ -42,7 +42,10 @@ constexpr int TAIL_THREADS = 512;  // narrow kernel CTA
 constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_NU = 128;       // bidder count at which the single-CTA kernel takes over
 constexpr int JV_THREADS = 1024;
-constexpr int LIST_K = 128;        // candidate objects kept per person
+#ifndef MCD_LIST_K
+#define MCD_LIST_K 128
+#endif
+constexpr int LIST_K = MCD_LIST_K;  // candidate objects kept per person
 constexpr int CAND_T = 4;          // per-thread candidates kept during a row sweep
 constexpr int MAX_PHASES = 48;
 constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size
@@ -113,6 +116,7 @@ struct LapState {
   int* lvalid;               // [n] list built
   int* fail;                 // [n] list slots whose candidate list could not certify the top-2 this round
   int max_chunks;            // no-list mode: upper bound on CTAs sharing one row
+  int chunk_waves;           // list rebuilds: at most this many chunks per CTA per round
   int* done;                 // [n] chunks finished per list slot
   double* pv1;               // [grid slots] partial best / second / objects of split rows
   double* pv2;
@@ -714,8 +718,8 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       // chunks at >= 1024 objects and the partial slots within their arrays
       int nch = 1;
       if (nfail > 0 && s.list_k == LIST_K) {
-        while (nch < 16 && nch * nfail < 2 * (int)gridDim.x && 2 * nch * nfail <= MAX_GRID_SLOTS &&
-               s.m / (2 * nch) >= 1024)
+        const int item_cap = (int)gridDim.x * s.chunk_waves;
+        while (nch < 16 && 2 * nch * nfail <= item_cap && 2 * nch * nfail <= MAX_GRID_SLOTS && s.m / (2 * nch) >= 1024)
           nch *= 2;
       }
       if (nch == 1) {
@@ -2052,6 +2056,11 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     if (min_chunk < 2) min_chunk = 2;
     int64_t mc2 = m / min_chunk;
     s.max_chunks = (int)(mc2 < 1 ? 1 : (mc2 > 256 ? 256 : mc2));
+  }
+  {
+    const char* e3 = getenv("MCD_LAP_CHUNK_WAVES");
+    s.chunk_waves = e3 ? atoi(e3) : 1;  // swept at 10k x 50k: 1 -> 554 ms, 2 -> 570, 4 -> 577 (whole solver)
+    if (s.chunk_waves < 1) s.chunk_waves = 1;
   }
   s.sp = reinterpret_cast<double*>(take(m * 8));
   s.pred = reinterpret_cast<int*>(take(m * 4));

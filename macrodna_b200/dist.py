@@ -185,19 +185,30 @@ class ShardedCell2Cell:
         return out
 
 
-def sweep_assignments(handle, rna: np.ndarray, dna: np.ndarray, replicate_cols, world=1, rank=0, precision="ozaki"):
+def sweep_assignments(handle, rna: np.ndarray, dna: np.ndarray, replicate_cols, world=1, rank=0, precision="ozaki",
+                      reuse_corr=True):
     """Resampling-stability sweep (config 4; reference
     ``Resampling_stability_analyses/CRC_data_analyses/clonal_proportions_resampling.py:172-201``):
-    replicate r re-runs the whole hot path on ``dna[replicate_cols[r]]`` (DNA cells resampled with
-    replacement).  Replicas only: rank ``r mod world`` runs replicate r, no collective.
+    replicate r is the hot path on ``dna[replicate_cols[r]]`` (DNA cells resampled with replacement).
+    Replicas only: rank ``r mod world`` runs replicate r, no collective.
+
+    ``reuse_corr`` (declared optimisation): a replicate only gathers DNA cells and the genes are
+    untouched, so its correlation matrix is a column gather of the base matrix -- the base matrix is computed once
+    per rank and every replicate runs ``mcd_subinstance_steps`` on it (same values bit for bit: the same kernel
+    computed them).  ``reuse_corr=False`` recomputes everything per replicate like the reference does.
     Returns {replicate index: (assign, step, objs)} for this rank's replicates.
     """
     out = {}
     M, G = rna.shape
-    for r, cols in enumerate(replicate_cols):
-        if replicate_owner(r, world) != rank:
-            continue
-        sub = np.ascontiguousarray(dna[np.asarray(cols)])
-        assign, step, objs, _ = handle.cell2cell(rna, sub, M, sub.shape[0], G, precision=precision)
+    mine = [r for r in range(len(replicate_cols)) if replicate_owner(r, world) == rank]
+    if reuse_corr and mine:
+        handle.cell2cell(rna, dna, M, dna.shape[0], G, precision=precision)
+    for r in mine:
+        cols = np.asarray(replicate_cols[r])
+        if reuse_corr:
+            assign, step, objs, _ = handle.subinstance(None, cols, M=M, N=dna.shape[0])
+        else:
+            sub = np.ascontiguousarray(dna[cols])
+            assign, step, objs, _ = handle.cell2cell(rna, sub, M, sub.shape[0], G, precision=precision)
         out[r] = (assign, step, objs)
     return out
