@@ -179,7 +179,7 @@ class Handle:
         self.check(self.lib.mcd_synchronize(self.h))
 
     # ---- whole path, host or device buffers -------------------------------------------------
-    def cell2cell(self, rna, dna, M, N, G, ld_rna=None, ld_dna=None, in_space=MEM_HOST, precision="fp64",
+    def cell2cell(self, rna, dna, M, N, G, ld_rna=None, ld_dna=None, in_space=MEM_HOST, precision="ozaki",
                   assign=None, step=None, step_obj=None, corr_out=None, out_space=MEM_HOST, rna_gene_idx=None,
                   dna_gene_idx=None):
         """``rna``/``dna``: numpy arrays (host) or integer device pointers; cells x genes float64.
