@@ -195,6 +195,28 @@ def cpu_baseline(M, N, G, clones, budget_s=20.0):
                 m0, n0, m1, n1, m2, n2, G, M, N, G, tc1, cores, tl0, tl1, tl2, expo)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner comes from C code
+    at the first collective), so stdout is handed to stderr for the run and the line is written to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -213,7 +235,7 @@ def run_reference_arm(args):
             "config": {"workload": "%s: %d RNA x %d DNA x %d genes" % (args.workload, M, N, G)},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,6 +253,7 @@ def main():
     ap.add_argument("--no-split", "--no-companions", dest="no_split", action="store_true",
                     help="skip the companion measurements of the other precision modes")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -310,7 +333,8 @@ def main():
     dna_host.copy_(dna)
     torch.cuda.synchronize()
     ms_e2e, res_e2e, _ = timed(lambda: runner.run_host(rna_host, dna_host), 1, K)
-    h2d = rna_host.numel() * 8 + dna_host.numel() * 8
+    # bytes crossing PCIe per step, summed over the ranks: every RNA row and (N > 1: every DNA row) exactly once
+    h2d = (M + N) * G * 8 if world > 1 else rna_host.numel() * 8 + dna_host.numel() * 8
     d2h = M * 4 * 2 + res_e2e["objs"].size * 8
 
     companions = None
@@ -431,7 +455,7 @@ def main():
             line["precision_modes"] = companions
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(M, N, G, clones)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 

@@ -170,18 +170,25 @@ class ShardedCell2Cell:
             return self._single(rna_host.data_ptr(), dna_host.data_ptr(), _lib.MEM_HOST)
         b = self._alloc()
         ext = torch.cuda.ExternalStream(self.h.lib.mcd_stream(self.h.h), device=self.device)
+        dlo, dhi = row_shard(self.N, self.world, self.rank)
+        per_d = -(-self.N // self.world)
         if b["rna_dev"] is None:
             b["rna_dev"] = torch.empty(rna_host.shape, dtype=torch.float64, device=self.device)
-            b["dna_dev"] = torch.empty(dna_host.shape, dtype=torch.float64, device=self.device)
+            b["dna_part"] = torch.zeros((per_d, self.G), dtype=torch.float64, device=self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ext):
             e0.record(ext)
-            b["dna_dev"].copy_(dna_host, non_blocking=True)
+            # every rank needs the whole DNA operand, but only 1/P of it crosses ITS PCIe link: the rest arrives
+            # over NVLink (all-gather of the raw row shards), which is ~10x faster than P redundant host copies
+            if dhi > dlo:
+                b["dna_part"][: dhi - dlo].copy_(dna_host[dlo:dhi], non_blocking=True)
             b["rna_dev"].copy_(rna_host, non_blocking=True)
+            dna_dev = gather_rows(b["dna_part"], self.N, self.world)
             e1.record(ext)
-        out = self._sharded(b["rna_dev"], b["dna_dev"])
+        out = self._sharded(b["rna_dev"], dna_dev)
         out["stats"]["ms_h2d"] = e0.elapsed_time(e1)
         out["stats"]["ms_total"] += out["stats"]["ms_h2d"]
+        out["h2d_bytes"] = int(rna_host.numel() * 8 + (dhi - dlo) * self.G * 8)
         return out
 
 
