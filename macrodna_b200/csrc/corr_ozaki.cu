@@ -28,6 +28,8 @@
 // slice tiles per k-block for 3 + 7 + 11 products.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "mcd_internal.cuh"
 
 namespace {
@@ -158,6 +160,7 @@ struct OzParams {
   double* Ct;
   int64_t ldct;
   unsigned int* wave_counter;  // zeroed before the launch
+  int align_mode;              // 0 free-running, 1 align the producers per wave, 2 per wave and pass
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -216,22 +219,25 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // DRAM reads, L2 hit rate 45 %).  So the leaders' producers start each wave together; inside a wave the
         // pairs keep each other in step (whoever is ahead takes the DRAM misses, the others hit L2 and catch up).
         // All CTAs are co-resident (grid <= #SMs, 1 CTA/SM), so the spin cannot deadlock.
-        if (leader && tile != pair) {
-          const int wave = (tile - pair) / num_pairs;
-          wave_target += (unsigned int)min(num_pairs, num_tiles - wave * num_pairs);
+        const int wave = (tile - pair) / num_pairs;
+        const unsigned int wave_pairs = (unsigned int)min(num_pairs, num_tiles - wave * num_pairs);
+        auto align = [&]() {
+          wave_target += wave_pairs;
           asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_counter) : "memory");
           unsigned int seen;
           do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_counter) : "memory");
             if ((int)(seen - wave_target) < 0) __nanosleep(200);
           } while ((int)(seen - wave_target) < 0);
-        }
+        };
+        if (leader && tile != pair && p.align_mode >= 1) align();
         int tm, tn;
         decode_tile(tile, p.tiles_m, p.tiles_n, tm, tn);
         const int row0 = tm * TM + (int)cta_rank * HALF;
         const int col0 = tn * TN + (int)cta_rank * HALF;
         for (int ps = npass - 1; ps >= 0; --ps) {
           const int nload = min(p.nsl, 2 * ps + 2);  // slices 0 .. nload-1 take part in the groups 2ps, 2ps+1
+          if (leader && ps != npass - 1 && p.align_mode >= 2) align();  // also re-align at every pass
           for (int kb = 0; kb < p.num_kb; ++kb) {
             for (int t = 0; t < nload; ++t) {
               mbar_wait(empty_bar + 8 * u, phase ^ 1);
@@ -432,13 +438,14 @@ int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int
   p.Ct = Ct;
   p.ldct = ldct;
   p.wave_counter = reinterpret_cast<unsigned int*>(h->d_flags + 8);
+  {
+    const char* e = getenv("MCD_OZAKI_ALIGN");
+    p.align_mode = e ? atoi(e) : 1;
+  }
   MCD_CUDA(h, cudaMemsetAsync(p.wave_counter, 0, sizeof(unsigned int), h->stream));
   MCD_CUDA(h, cudaFuncSetAttribute(corr_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  const int64_t max_pairs = h->sm_count / 2;
-  const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = h->stream;
@@ -449,6 +456,15 @@ int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // the wave alignment spins on peers, so every CTA pair of the grid must be resident at once
+  cfg.gridDim = dim3(h->sm_count & ~1);
+  int resident_pairs = 0;
+  MCD_CUDA(h, cudaOccupancyMaxActiveClusters(&resident_pairs, corr_ozaki_kernel, &cfg));
+  if (resident_pairs < 1) return mcd_fail(h, MCD_ERR_CUDA, "corr_ozaki_kernel: no CTA pair can be resident");
+  int64_t max_pairs = h->sm_count / 2;
+  if (resident_pairs < max_pairs) max_pairs = resident_pairs;
+  const int grid = 2 * (int)(tiles < max_pairs ? tiles : max_pairs);
+  cfg.gridDim = dim3(grid);
   MCD_CUDA(h, cudaLaunchKernelEx(&cfg, corr_ozaki_kernel, ma, mb, p));
   h->launches++;
   return MCD_OK;
