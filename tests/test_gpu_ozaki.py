@@ -125,3 +125,50 @@ def test_whole_path_ozaki(handle, name):
     ident, rep = tie_report(c_ref, assign, step, a_ref, s_ref, rel=1e-9)
     assert ident, rep
     assert np.abs(objs - o_ref).max() <= 1e-9 * np.abs(o_ref).max()
+
+
+def test_ozaki_long_rows_and_fp64_fallback(handle):
+    """G > 24 576 takes K1's three-sweep variant (digits included); G beyond the exact-int32 bound of the integer
+    path (nsl * 4096 * ldk8 < 2^31) silently takes the FP64 tensor pipe instead -- both still device paths."""
+    from oracle import restatement as R
+
+    rng = np.random.default_rng(21)
+    for G, tol in ((30000, 1e-12), (90000, 1e-12)):
+        rna = np.log1p(rng.poisson(3.0, size=(40, G)).astype(np.float64))
+        dna = np.log1p(rng.integers(1, 5, size=(17, G)) * (1 + 0.05 * rng.standard_normal((17, G))))
+        corr = np.empty((40, 17))
+        assign, step, objs, _ = handle.cell2cell(rna, dna, 40, 17, G, precision="ozaki", corr_out=corr)
+        c_ref, a_ref, s_ref, o_ref = R.cell2cell_arrays(rna, dna)
+        assert np.abs(corr - c_ref).max() < tol
+        assert (assign == a_ref).all() and (step == s_ref).all()
+
+
+def test_ozaki_chunked_host_input_equals_device_input(handle):
+    """Host buffers above 768 MB are staged in tile-aligned RNA chunks overlapped with K1 + K2c; the result must be
+    bit-identical to the one-shot device-input path (same kernels, same tiles)."""
+    torch = _torch()
+    from macrodna_b200 import _lib
+
+    rng = np.random.default_rng(2)
+    M, N, G = 5300, 300, 20000
+    rna = np.log1p(rng.poisson(2.0, size=(M, G)).astype(np.float64))
+    dna = np.log1p(rng.integers(1, 5, size=(N, G)) * (1 + 0.05 * rng.standard_normal((N, G))))
+    c_host = np.empty((M, N))
+    a1, s1, o1, st1 = handle.cell2cell(rna, dna, M, N, G, precision="ozaki", corr_out=c_host)
+    d_r, d_d = torch.from_numpy(rna).cuda(), torch.from_numpy(dna).cuda()
+    c_dev = np.empty((M, N))
+    a2, s2, o2, st2 = handle.cell2cell(d_r.data_ptr(), d_d.data_ptr(), M, N, G, in_space=_lib.MEM_DEVICE,
+                                       precision="ozaki", corr_out=c_dev)
+    assert (c_host == c_dev).all() and (a1 == a2).all() and (s1 == s2).all() and (o1 == o2).all()
+    assert st1.ms_h2d >= 0.0 and st1.kernel_launches > st2.kernel_launches  # more K1 / K2c launches: chunks
+
+
+def test_ozaki_nonfinite_input_raises(handle):
+    rng = np.random.default_rng(4)
+    rna = rng.random((20, 300))
+    dna = rng.random((9, 300))
+    rna[3, 17] = np.nan
+    with pytest.raises(ValueError):
+        handle.cell2cell(rna, dna, 20, 9, 300, precision="ozaki")
+    rna[3, 17] = 0.5
+    handle.cell2cell(rna, dna, 20, 9, 300, precision="ozaki")  # the flag was cleared
