@@ -41,12 +41,18 @@ constexpr int BK = 64;                  // int8 elements = 64 bytes = one swizzl
 constexpr int UMMA_K = 32;
 constexpr int TILE_BYTES = HALF * BK;   // 8 KB: one digit slice of one operand half
 constexpr int UNIT_BYTES = 2 * TILE_BYTES;
-constexpr int UNITS = 12;
+#ifndef MCD_OZ_UNITS
+#define MCD_OZ_UNITS 12
+#endif
+#ifndef MCD_OZ_BAND
+#define MCD_OZ_BAND 6
+#endif
+constexpr int UNITS = MCD_OZ_UNITS;
 constexpr int SMEM_BYTES = UNITS * UNIT_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int NUM_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int BAND_M = 8;
+constexpr int BAND_M = MCD_OZ_BAND;
 
 // instruction descriptor, kind::i8: D = S32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9, 10-12 = 1),
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
