@@ -423,7 +423,8 @@ def main():
                 rooflines["corr"]["traffic"] = tr[corr_kernel][0]
             if "lap_auction_kernel" in tr:
                 rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
-                rooflines["lap"]["traffic_note"] = "one wide-round launch (step 1) of lap_auction_kernel"
+                rooflines["lap"]["traffic_note"] = ("one wide-round launch (step 2) of lap_auction_kernel; ncu returned no DRAM "
+                                                    "counters for the step-1 launch and the cluster kernels")
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_rows", "corr": corr_kernel,
