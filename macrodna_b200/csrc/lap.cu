@@ -169,17 +169,48 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
   top2_push(a, b.v1, b.j1);
   top2_push(a, b.v2, b.j2);
 }
+// ---- warp-level selection through redux.sync ------------------------------------------------------------
+// The narrow rounds are one dependent chain, and ncu's source view put most of the working warp's time into the
+// shuffle-and-branch top-2 butterfly (5 levels x 6 shuffles x two branchy double compares).  An arg-max over the warp
+// is three integer warp reductions instead: the doubles are mapped to order-preserving 64-bit keys, the high
+// words, the low words among the lanes that tie on the high word, and the object index among the lanes that tie on
+// both are reduced with redux.sync.  Same total order as better(): larger value first, smaller index on ties.
+__device__ __forceinline__ unsigned long long f64_sortable(double v) {
+  const long long b = __double_as_longlong(v + 0.0);  // -0.0 -> +0.0: equal doubles get equal keys
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double sortable_f64(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+// every lane returns the best key, its index, and the lane that held it
+__device__ __forceinline__ void warp_argmax_key(unsigned long long key, int j, unsigned long long& kbest, int& jbest,
+                                                int& wlane) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const bool c1 = hi == mh;
+  const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+  const bool c2 = c1 && lo == ml;
+  const unsigned mj = __reduce_min_sync(0xffffffffu, c2 ? (unsigned)j : 0xffffffffu);  // j = -1 (nothing) loses ties
+  kbest = ((unsigned long long)mh << 32) | ml;
+  jbest = (int)mj;
+  wlane = __ffs(__ballot_sync(0xffffffffu, c2 && (unsigned)j == mj)) - 1;
+}
+// Top-2 over the warp of per-lane sorted pairs (objects are distinct across lanes): the best is the best of the
+// lanes' firsts; the runner-up is the best of {the winner lane's second, the other lanes' firsts}.
 __device__ __forceinline__ Top2 top2_warp_reduce(Top2 t) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Top2 r;
-    r.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
-    r.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
-    r.j1 = __shfl_xor_sync(0xffffffffu, t.j1, o);
-    r.j2 = __shfl_xor_sync(0xffffffffu, t.j2, o);
-    top2_merge(t, r);
-  }
-  return t;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long k1 = f64_sortable(t.v1), k2 = f64_sortable(t.v2);
+  unsigned long long kb1, kb2;
+  int jb1, jb2, w1, w2;
+  warp_argmax_key(k1, t.j1, kb1, jb1, w1);
+  warp_argmax_key(lane == w1 ? k2 : k1, lane == w1 ? t.j2 : t.j1, kb2, jb2, w2);
+  Top2 r;
+  r.v1 = sortable_f64(kb1);
+  r.j1 = jb1;
+  r.v2 = sortable_f64(kb2);
+  r.j2 = jb2;
+  return r;
 }
 
 __device__ __forceinline__ unsigned long long pack_bid(double gamma, int person) {
@@ -346,15 +377,11 @@ __device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* c
 
 // warp-wide arg-max of (v, j) with the smaller index winning ties; every lane returns the winner
 __device__ __forceinline__ void warp_argmax(double& v, int& j) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, j, o);
-    if (ov > v || (ov == v && (unsigned)oj < (unsigned)j)) {
-      v = ov;
-      j = oj;
-    }
-  }
+  unsigned long long kb;
+  int jb, w;
+  warp_argmax_key(f64_sortable(v), j, kb, jb, w);
+  v = sortable_f64(kb);
+  j = jb;
 }
 
 // Same contract as chunk_scan_build below for kc <= 16 (many short chunks), without the shared-memory sort:
