@@ -139,31 +139,29 @@ struct Top2 {
   int j1, j2;
 };
 
+// Written with non-short-circuit operators and selects: these run inside one-warp dependent chains, where a
+// divergent double-compare branch costs more than the few redundant instructions.
 __device__ __forceinline__ bool better(double va, int ja, double vb, int jb) {
-  return va > vb || (va == vb && ja < jb);
+  return (va > vb) | ((va == vb) & (ja < jb));
 }
 __device__ __forceinline__ void top2_push(Top2& t, double v, int j) {
-  if (better(v, j, t.v1, t.j1)) {
-    t.v2 = t.v1;
-    t.j2 = t.j1;
-    t.v1 = v;
-    t.j1 = j;
-  } else if (better(v, j, t.v2, t.j2)) {
-    t.v2 = v;
-    t.j2 = j;
-  }
+  const bool b1 = better(v, j, t.v1, t.j1), b2 = better(v, j, t.v2, t.j2);
+  const double nv2 = b1 ? t.v1 : (b2 ? v : t.v2);
+  const int nj2 = b1 ? t.j1 : (b2 ? j : t.j2);
+  t.v1 = b1 ? v : t.v1;
+  t.j1 = b1 ? j : t.j1;
+  t.v2 = nv2;
+  t.j2 = nj2;
 }
 // in-thread variant: candidates arrive in increasing j, so strict '>' keeps the smallest index on ties
 __device__ __forceinline__ void top2_push_seq(Top2& t, double v, int j) {
-  if (v > t.v1) {
-    t.v2 = t.v1;
-    t.j2 = t.j1;
-    t.v1 = v;
-    t.j1 = j;
-  } else if (v > t.v2) {
-    t.v2 = v;
-    t.j2 = j;
-  }
+  const bool b1 = v > t.v1, b2 = v > t.v2;
+  const double nv2 = b1 ? t.v1 : (b2 ? v : t.v2);
+  const int nj2 = b1 ? t.j1 : (b2 ? j : t.j2);
+  t.v1 = b1 ? v : t.v1;
+  t.j1 = b1 ? j : t.j1;
+  t.v2 = nv2;
+  t.j2 = nj2;
 }
 __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
   top2_push(a, b.v1, b.j1);
@@ -1308,13 +1306,24 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
     __syncthreads();
     const long long c1 = clock64();
     // ---- 2. thread b merges the 16 warp partials of bidder b and ships the CTA partial to CTA 0
-    if (tid < nu) {
-      Top2 a = wpart[tid * TAIL_WARPS];
-      for (int w = 1; w < G; ++w) top2_merge(a, wpart[tid * TAIL_WARPS + w]);
-      const uint32_t dst = map_to_cta(smem_addr(&cpart[tid * CL_MAX_CS + cta]), 0);
-      const uint32_t rbar = map_to_cta(barA, 0);
-      st_async_v2(dst, __double_as_longlong(a.v1), __double_as_longlong(a.v2), rbar);
-      st_async_v2(dst + 16, ((uint64_t)(uint32_t)a.j2 << 32) | (uint32_t)a.j1, 0ull, rbar);
+    //         (G > 1: warp b reduces bidder b's G partials with the redux arg-max; G == 1: nothing to merge)
+    if (G > 1 ? warp < nu : tid < nu) {
+      Top2 a;
+      int b;
+      if (G > 1) {
+        b = warp;
+        a = lane < G ? wpart[b * TAIL_WARPS + lane] : Top2{NEG_INF, NEG_INF, -1, -1};
+        a = top2_warp_reduce(a);
+      } else {
+        b = tid;
+        a = wpart[b * TAIL_WARPS];
+      }
+      if (G == 1 || lane == 0) {
+        const uint32_t dst = map_to_cta(smem_addr(&cpart[b * CL_MAX_CS + cta]), 0);
+        const uint32_t rbar = map_to_cta(barA, 0);
+        st_async_v2(dst, __double_as_longlong(a.v1), __double_as_longlong(a.v2), rbar);
+        st_async_v2(dst + 16, ((uint64_t)(uint32_t)a.j2 << 32) | (uint32_t)a.j1, 0ull, rbar);
+      }
     }
     // ---- 3. CTA 0, warp 0: merge over CTAs, resolve, multicast the round packet
     if (cta == 0 && warp == 0) {
@@ -1323,7 +1332,17 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
       tq[1] += c2 - c1;
       const bool live = lane < nu;
       Top2 a{NEG_INF, NEG_INF, -1, -1};
-      if (live) {
+      if (nu <= 4) {  // few bidders (the usual case): one redux reduction per bidder over the CTAs' partials
+        for (int bb = 0; bb < nu; ++bb) {
+          Top2 q{NEG_INF, NEG_INF, -1, -1};
+          if (lane < (int)ncta) {
+            const TailPart& pq = cpart[bb * CL_MAX_CS + lane];
+            q = Top2{pq.v1, pq.v2, pq.j1, pq.j2};
+          }
+          q = top2_warp_reduce(q);
+          if (lane == bb) a = q;
+        }
+      } else if (live) {
         for (uint32_t c = 0; c < ncta; ++c) {
           const TailPart& q = cpart[lane * CL_MAX_CS + c];
           top2_merge(a, Top2{q.v1, q.v2, q.j1, q.j2});
