@@ -31,6 +31,7 @@
 //
 // Bound: HBM bandwidth for the row sweeps (8 B per object), L2/launch latency for the narrow rounds.
 #include <cstdlib>
+#include <type_traits>
 
 #include "mcd_internal.cuh"
 
@@ -1270,35 +1271,41 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
     for (int b = warp / G; b < nu; b += per_pass) {
       const double* wrow = s.W + (int64_t)s_list[b] * s.ldw;
       Top2 t{NEG_INF, NEG_INF, -1, -1};
-      int j = ws + 2 * lane;
       if (s.vec) {
-        for (; j + 15 * 64 + 1 < we; j += 16 * 64) {  // 16 independent 128-bit loads in flight per lane
-          double2 wv[16];
+        // every load of a batch is issued before the first use (guards instead of a scalar tail loop: a short
+        // sub-slice -- 78 objects per warp on the 10k x 10k square step -- must cost ONE memory latency, not two)
+        auto batch = [&](auto depth_tag) {
+          constexpr int D = decltype(depth_tag)::value;
+          for (int j = ws + 2 * lane; j < we; j += D * 64) {
+            double2 wv[D];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + j + u * 64));
+            for (int u = 0; u < D; ++u) {
+              const int jj = j + u * 64;
+              wv[u] = make_double2(NEG_INF, NEG_INF);
+              if (jj + 1 < we)
+                wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + jj));
+              else if (jj < we)
+                wv[u].x = __ldg(wrow + jj);
+            }
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const double2 pv = *reinterpret_cast<const double2*>(sprice + (j + u * 64 - o0));
-            top2_push_seq(t, wv[u].x - pv.x, j + u * 64);
-            top2_push_seq(t, wv[u].y - pv.y, j + u * 64 + 1);
+            for (int u = 0; u < D; ++u) {
+              const int jj = j + u * 64;
+              if (jj + 1 < we) {
+                const double2 pv = *reinterpret_cast<const double2*>(sprice + (jj - o0));
+                top2_push_seq(t, wv[u].x - pv.x, jj);
+                top2_push_seq(t, wv[u].y - pv.y, jj + 1);
+              } else if (jj < we) {
+                top2_push_seq(t, wv[u].x - sprice[jj - o0], jj);
+              }
+            }
           }
-        }
-        for (; j + 7 * 64 + 1 < we; j += 8 * 64) {  // 8 independent 128-bit loads in flight per lane
-          double2 wv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + j + u * 64));
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const double2 pv = *reinterpret_cast<const double2*>(sprice + (j + u * 64 - o0));
-            top2_push_seq(t, wv[u].x - pv.x, j + u * 64);
-            top2_push_seq(t, wv[u].y - pv.y, j + u * 64 + 1);
-          }
-        }
-      }
-      for (; j < we; j += 64) {
-        const double a0 = __ldg(wrow + j) - sprice[j - o0];
-        top2_push_seq(t, a0, j);
-        if (j + 1 < we) top2_push_seq(t, __ldg(wrow + j + 1) - sprice[j + 1 - o0], j + 1);
+        };
+        if (we - ws <= 128)
+          batch(std::integral_constant<int, 2>{});
+        else
+          batch(std::integral_constant<int, 8>{});
+      } else {
+        for (int j = ws + lane; j < we; j += 32) top2_push_seq(t, __ldg(wrow + j) - sprice[j - o0], j);
       }
       t = top2_warp_reduce(t);
       if (lane == 0) wpart[b * TAIL_WARPS + g] = t;
