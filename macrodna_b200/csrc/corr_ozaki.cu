@@ -322,6 +322,7 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tempty_leader = map_to_cta(tempty_bar, 0);
     double* const P = p.C ? p.C : p.Ct;  // where the FP64 partial sums live between passes
     const bool p_is_c = p.C != nullptr;
+    const bool c_vec = p_is_c && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     uint32_t tphase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int tm, tn;
@@ -347,6 +348,38 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (row_ok) {
             const int64_t col0 = (int64_t)tn * TN + half * HALF + c * 32;
+            if (p_is_c && c_vec && col0 + 32 <= p.N) {
+              // whole 32-column chunk inside the matrix: 128-bit accesses, all partial-sum loads issued up front
+              double2* prow = reinterpret_cast<double2*>(P + row * p.ldc + col0);
+              double2 acc[16];
+              if (!first) {
+#pragma unroll
+                for (int q2 = 0; q2 < 16; ++q2) acc[q2] = prow[q2];
+              }
+#pragma unroll
+              for (int q2 = 0; q2 < 16; ++q2) {
+                double v0 = (double)(int)r0[2 * q2] * w0, v1 = (double)(int)r0[2 * q2 + 1] * w0;
+                if (two) {
+                  v0 += (double)(int)r1[2 * q2] * w1;
+                  v1 += (double)(int)r1[2 * q2 + 1] * w1;
+                }
+                if (!first) {
+                  v0 += acc[q2].x;
+                  v1 += acc[q2].y;
+                }
+                if (last) {
+                  const int64_t col = col0 + 2 * q2;
+                  const double nn0 = na * __ldg(p.nB + col), nn1 = na * __ldg(p.nB + col + 1);
+                  v0 = v0 * (sa * __ldg(p.sB + col) * (1.0 / 4096.0)) * (nn0 / (1e-10 + nn0));
+                  v1 = v1 * (sa * __ldg(p.sB + col + 1) * (1.0 / 4096.0)) * (nn1 / (1e-10 + nn1));
+                  if (p.Ct) {
+                    p.Ct[col * p.ldct + row] = v0;
+                    p.Ct[(col + 1) * p.ldct + row] = v1;
+                  }
+                }
+                prow[q2] = make_double2(v0, v1);
+              }
+            } else {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               const int64_t col = col0 + q;
@@ -365,6 +398,7 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   P[pi] = v;
                 }
               }
+            }
             }
           }
         }
