@@ -15,6 +15,8 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -56,6 +58,16 @@ __device__ __forceinline__ double group_max(double v, double* red) {
 #pragma unroll
   for (int w = 0; w < WPG; ++w) s = fmax(s, red[g0 + w]);
   return s;
+}
+
+// A zero-variance cell must standardise to EXACTLY zero (reference: its correlations are exactly 0.0, SURVEY
+// App. B), but sum/G need not reproduce the constant bit for bit, which would leave a row of identical rounding
+// residues with a non-zero norm.  A row whose centred sum of squares is at rounding level relative to its mean
+// (every residue below 2^-45 |mean|: nothing but the rounding of the mean) is therefore declared zero-variance:
+// norm 0, unit row / digits / centred row all zero.
+__device__ __forceinline__ bool flat_row(double ss, double mean, int G) {
+  const double r = mean * 0x1p-45;
+  return ss <= (double)G * r * r;
 }
 
 // Integer-slice operand of the int8 tensor-core path (corr_ozaki.cu).  y (|y| < 0.5) is rounded to the
@@ -140,6 +152,8 @@ standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int
     ss += cx * cx + cy * cy;
   }
   ss = group_sum<T, BLOCK>(ss, red);
+  const bool flat = flat_row(ss, mean, G);
+  if (flat) ss = 0.0;  // zero-variance cell: norm 0, every output below becomes exactly zero
   const double nrm = sqrt(ss);
   double amax = 0.0;
   if (oz.digits != nullptr) {  // uniform over the block
@@ -190,9 +204,9 @@ standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int
     for (int k = 0; k < NV; ++k) {
       const int e = 2 * (t + k * T);
       if (e + 1 < G) {
-        *reinterpret_cast<double2*>(y + e) = v[k];  // ldk is a multiple of 16 -> aligned
+        *reinterpret_cast<double2*>(y + e) = flat ? make_double2(0.0, 0.0) : v[k];  // ldk % 16 == 0 -> aligned
       } else if (e < G) {
-        y[e] = v[k].x;
+        y[e] = flat ? 0.0 : v[k].x;
       }
     }
     for (int64_t c = G + t; c < ldk; c += T) y[c] = 0.0;
@@ -221,6 +235,172 @@ standardize_rows(const double* __restrict__ X, const int* __restrict__ gidx, int
   }
 }
 
+// ---- digit-slice fast path (the default precision mode) ---------------------------------------------------------
+// Same arithmetic as the digit branch of standardize_rows, restructured so that the kernel stays on the HBM
+// roofline instead of the issue slots (ncu of the generic kernel: 128 instructions per element, 47 % of the copy
+// bandwidth):
+//   * a thread owns 4 CONSECUTIVE genes per sweep (one 256-bit ld.global.cs, LDG.256), so the four digits of one
+//     slice form one 32-bit word and a warp stores 128 contiguous bytes per slice;
+//   * NSL is a template parameter: every field offset is an immediate;
+//   * rounding to the fixed-point integer and adding the field bias is ONE fma with the constant
+//     1.5 * 2^52 + B (B = 64 in every 7-bit field): the low mantissa bits of the result are q + B
+//     (NSL <= 7: |q + B| < 2^51; 8 slices need 56 bits and keep cvt.rni.s64);
+//   * bytes are packed with PRMT, and  ((w & 0x7f7f7f7f) + 0x40404040) ^ 0x80808080  turns the four biased
+//     fields d + 64 into the int8 digits d  (no carry can cross a byte: d + 128 <= 191).
+template <int NSL>
+__device__ __forceinline__ void ozaki_bits(double c, double mul, double magic, uint32_t& lo, uint32_t& hi) {
+  if (NSL <= 7) {
+    const long long b = __double_as_longlong(fma(c, mul, magic));
+    lo = (uint32_t)b;
+    hi = (uint32_t)((unsigned long long)b >> 32);
+  } else {
+    const unsigned long long B = (0x0102040810204081ull << 6) & ((1ull << (7 * NSL)) - 1ull);
+    const unsigned long long qb = (unsigned long long)__double2ll_rn(c * mul) + B;
+    lo = (uint32_t)qb;
+    hi = (uint32_t)(qb >> 32);
+  }
+}
+
+template <int OFF>
+__device__ __forceinline__ uint32_t ozaki_field(uint32_t lo, uint32_t hi) {  // low 7 bits = field at bit OFF
+  if constexpr (OFF == 0)
+    return lo;
+  else if constexpr (OFF + 7 <= 32)
+    return lo >> OFF;
+  else if constexpr (OFF >= 32)
+    return hi >> (OFF - 32);
+  else
+    return __funnelshift_r(lo, hi, OFF);
+}
+
+template <int NSL, int SL>
+__device__ __forceinline__ void ozaki_store_slices(const uint32_t (&lo)[4], const uint32_t (&hi)[4], int8_t* o,
+                                                   int64_t slice_stride) {
+  if constexpr (SL < NSL) {
+    constexpr int OFF = 7 * (NSL - 1 - SL);
+    const uint32_t w01 = __byte_perm(ozaki_field<OFF>(lo[0], hi[0]), ozaki_field<OFF>(lo[1], hi[1]), 0x0040);
+    const uint32_t w23 = __byte_perm(ozaki_field<OFF>(lo[2], hi[2]), ozaki_field<OFF>(lo[3], hi[3]), 0x0040);
+    const uint32_t w = __byte_perm(w01, w23, 0x5410);
+    *reinterpret_cast<uint32_t*>(o + SL * slice_stride) = ((w & 0x7f7f7f7fu) + 0x40404040u) ^ 0x80808080u;
+    ozaki_store_slices<NSL, SL + 1>(lo, hi, o, slice_stride);
+  }
+}
+
+// T threads per row, NV4 sweeps of 4 genes per thread (row capacity 4*T*NV4 >= ldk8), digit output only.
+// vec: X is 32-byte aligned and ldx a multiple of 4 (256-bit loads legal).
+template <int T, int NV4, int NSL>
+__global__ void __launch_bounds__(512, 1)
+standardize_digits(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int G, int64_t ldx,
+                   int vec, double* __restrict__ norms, int* __restrict__ flags, const mcd_ozaki_out oz) {
+  constexpr int BLOCK = 512;
+  constexpr int ROWS = BLOCK / T;
+  __shared__ double red[BLOCK / 32];
+  const int t = threadIdx.x % T;
+  const int64_t row = (int64_t)blockIdx.x * ROWS + threadIdx.x / T;
+  const bool live = row < ncells;
+  const double* x = X + (live ? row : 0) * ldx;
+
+  double v[NV4][4];
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int e = 4 * (t + k * T);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (live && e < G) {
+      if (gidx != nullptr) {
+        a0 = __ldg(x + __ldg(gidx + e));
+        if (e + 1 < G) a1 = __ldg(x + __ldg(gidx + e + 1));
+        if (e + 2 < G) a2 = __ldg(x + __ldg(gidx + e + 2));
+        if (e + 3 < G) a3 = __ldg(x + __ldg(gidx + e + 3));
+      } else if (vec && e + 3 < G) {
+        asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+                     : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
+                     : "l"(x + e));
+      } else {
+        a0 = __ldcs(x + e);
+        if (e + 1 < G) a1 = __ldcs(x + e + 1);
+        if (e + 2 < G) a2 = __ldcs(x + e + 2);
+        if (e + 3 < G) a3 = __ldcs(x + e + 3);
+      }
+    }
+    v[k][0] = a0;
+    v[k][1] = a1;
+    v[k][2] = a2;
+    v[k][3] = a3;
+    sum += (a0 + a1) + (a2 + a3);
+  }
+  sum = group_sum<T, BLOCK>(sum, red);
+  const double mean = sum / (double)G;
+
+  double ss = 0.0, amax = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int e = 4 * (t + k * T);
+    if (e + 3 < G) {  // whole group inside the row: no per-gene masks
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double c = v[k][i] - mean;
+        v[k][i] = c;
+        ss = fma(c, c, ss);
+        amax = (fabs(c) > amax) ? fabs(c) : amax;  // non-finite rows are flagged below: no NaN handling needed
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double c = (e + i < G) ? v[k][i] - mean : 0.0;
+        v[k][i] = c;
+        ss = fma(c, c, ss);
+        amax = (fabs(c) > amax) ? fabs(c) : amax;
+      }
+    }
+  }
+  ss = group_sum<T, BLOCK>(ss, red);
+  if (flat_row(ss, mean, G)) ss = 0.0;  // zero-variance cell: norm 0 -> mul 0 -> all digits zero
+  amax = group_max<T, BLOCK>(amax, red);
+  if (!live) return;
+  const double nrm = sqrt(ss);
+  if (t == 0) {
+    norms[row] = nrm;
+    if (!isfinite(sum) || !isfinite(ss)) atomicOr(flags, 1);
+  }
+  // unit row u = c / nrm scaled by 2^e so that max|u| * 2^e lies in [0.25, 0.5)
+  const double inv = (nrm > 0.0 && isfinite(nrm)) ? 1.0 / nrm : 0.0;
+  const double umax = amax * inv;
+  int ex = 0;
+  if (umax > 0.0 && isfinite(umax)) (void)frexp(umax, &ex);
+  const int sh = -ex - 1;
+  if (t == 0) oz.scale[row] = scalbn(1.0, -sh);
+  const double mul = inv * scalbn(1.0, sh + 7 * NSL - 1);
+  const unsigned long long B = (0x0102040810204081ull << 6) & ((1ull << (7 * NSL)) - 1ull);
+  const double magic = 6755399441055744.0 + (double)B;  // 1.5 * 2^52 + B, exact (B < 2^51 when NSL <= 7)
+  int8_t* o = oz.digits + row * oz.ldk8 + 4 * t;
+  const int ldk8 = (int)oz.ldk8;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int g = 4 * (t + k * T);
+    if (g < ldk8) {  // genes in [G, ldk8) are zero digits (c = 0 there)
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ozaki_bits<NSL>(v[k][i], mul, magic, lo[i], hi[i]);
+      ozaki_store_slices<NSL, 0>(lo, hi, o + 4 * k * T, oz.slice_stride);
+    }
+  }
+}
+
+template <int T, int NV4>
+int launch_digits(mcd_context* h, const double* X, const int* gidx, int64_t ncells, int G, int64_t ldx, double* norms,
+                  const mcd_ozaki_out& oz) {
+  constexpr int ROWS = 512 / T;
+  const unsigned grid = (unsigned)((ncells + ROWS - 1) / ROWS);
+  const int vec = ((reinterpret_cast<uintptr_t>(X) & 31) == 0) && ((ldx & 3) == 0);
+  if (oz.nsl == 6)
+    standardize_digits<T, NV4, 6><<<grid, 512, 0, h->stream>>>(X, gidx, ncells, G, ldx, vec, norms, h->d_flags, oz);
+  else
+    standardize_digits<T, NV4, 8><<<grid, 512, 0, h->stream>>>(X, gidx, ncells, G, ldx, vec, norms, h->d_flags, oz);
+  MCD_LAUNCH_CHECK(h, "standardize_digits");
+  return MCD_OK;
+}
+
 // Rows longer than the register-resident capacity: one 512-thread block per row, three sweeps
 // (the row stays L2-resident between sweeps; declared as a 3-read variant in DESIGN.md).
 __global__ void __launch_bounds__(512)
@@ -242,6 +422,8 @@ standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx
     ss += c * c;
   }
   ss = group_sum<512, 512>(ss, red);
+  const bool flat = flat_row(ss, mean, (int)(G < 2147483647 ? G : 2147483647));
+  if (flat) ss = 0.0;
   const double nrm = sqrt(ss);
   if (threadIdx.x == 0) {
     norms[row] = nrm;
@@ -250,7 +432,7 @@ standardize_rows_long(const double* __restrict__ X, const int* __restrict__ gidx
   const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
   if (Y != nullptr) {
     double* y = Y + row * ldk;
-    for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = e < G ? at(e) - mean : 0.0;
+    for (int64_t e = threadIdx.x; e < ldk; e += 512) y[e] = (e < G && !flat) ? at(e) - mean : 0.0;
   }
   if (oz.digits != nullptr) {
     double amax = 0.0;
@@ -311,6 +493,19 @@ int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int6
   if (ozaki != nullptr) oz = *ozaki;
   const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const int g = (int)G;
+  if (oz.digits != nullptr && centred == nullptr && slices == nullptr && (oz.nsl == 6 || oz.nsl == 8) &&
+      oz.ldk8 <= 24576 && (oz.ldk8 & 3) == 0 && (oz.slice_stride & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(oz.digits) & 3) == 0 && !(getenv("MCD_K1_GENERIC") && atoi(getenv("MCD_K1_GENERIC")))) {
+    const int64_t cap = oz.ldk8;  // the sweeps also write the zero padding up to ldk8
+    if (cap <= 256) return launch_digits<32, 2>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 1024) return launch_digits<128, 2>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 4096) return launch_digits<512, 2>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 8192) return launch_digits<512, 4>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 12288) return launch_digits<512, 6>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 16384) return launch_digits<512, 8>(h, X, gidx, ncells, g, ldx, norms, oz);
+    if (cap <= 20480) return launch_digits<512, 10>(h, X, gidx, ncells, g, ldx, norms, oz);
+    return launch_digits<512, 12>(h, X, gidx, ncells, g, ldx, norms, oz);
+  }
   if (G <= 256) return launch_t<32, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
   if (G <= 1024) return launch_t<128, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);
   if (G <= 4096) return launch_t<512, 4>(h, vec, X, gidx, ncells, g, ldx, centred, ldk, slices, slices_lo, ldk16, norms, oz);

@@ -16,13 +16,14 @@ for st in settings:
     for k, v in st.items():
         os.environ[k] = v
     for rep in range(2):
-        a, s_, o, stats = h.cell2cell(rna.data_ptr(), dna.data_ptr(), M, N, G, in_space=_lib.MEM_DEVICE)
+        a, s_, o, stats = h.cell2cell(rna.data_ptr(), dna.data_ptr(), M, N, G, in_space=_lib.MEM_DEVICE,
+                                       precision=os.environ.get("MCD_SWEEP_PRECISION", "ozaki"))
     d = stats.as_dict()
     if ref is None:
         ref = (a.copy(), o.copy())
     same = bool((a == ref[0]).all())
     print(json.dumps({"set": st, "ms_lap": round(d["ms_lap"], 2), "step_ms": [round(x, 2) for x in d["step_ms"]],
                       "rounds": d["step_rounds"], "bids": d["lap_bids"], "aug": [d["lap_aug_rows"], d["lap_aug_steps"]],
-                      "same_as_first": same, "cyc_per_round": [round(c / max(1, sum(d["step_rounds"]))) for c in d["lap_cycles"]], "ms_corr": round(d["ms_corr"], 2)}), flush=True)
+                      "same_as_first": same, "cyc_per_round": [round(c / max(1, sum(d["step_rounds"]))) for c in d["lap_cycles"]], "ms_corr": round(d["ms_corr"], 2), "ms_standardize": round(d["ms_standardize"], 3)}), flush=True)
     for k in st:
         del os.environ[k]
