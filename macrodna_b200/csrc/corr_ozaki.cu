@@ -66,6 +66,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// one elected lane of a converged warp arrives (the producer warp runs warp-uniformly, see umma_i8_2cta_pred)
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "r"(bytes)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -93,6 +104,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
       "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                                  int z) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5}], [%2];\n"
+      "}\n" ::"r"(dst),
       "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
@@ -124,6 +147,32 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+// The MMA warp runs its loops WARP-UNIFORMLY (all 32 lanes: ring slots, phases and descriptors then live in uniform
+// registers) and only the tcgen05 instructions themselves are predicated on one elected lane (elect.sync).  Inside an
+// `if (lane == 0)` region the compiler cannot prove the descriptors uniform and wraps every UTCIMMA in an
+// ELECT / R2UR.BROADCAST waterfall loop (~20 instructions + local-memory slot lookups per MMA).
+__device__ __forceinline__ void umma_i8_2cta_pred(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                                  uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_pred(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   __syncwarp();
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -150,6 +199,52 @@ __device__ __forceinline__ void decode_tile(int t, int tiles_m, int tiles_n, int
   const int hb = min(BAND_M, tiles_m - band * BAND_M);
   tn = rem / hb;
   tm = band * BAND_M + (rem - tn * hb);
+}
+
+// One pass of the MMA issuer over all k-blocks: NLOAD digit-slice units per k-block, NG significance groups
+// (g_lo = NLOAD - NG and, when NG = 2, g_lo + 1), fully unrolled -- the slot of every unit is a register.
+template <int NLOAD, int NG>
+__device__ __forceinline__ void mma_pass(const int num_kb, int& u, uint32_t& phase, const uint32_t smem_base,
+                                         const uint32_t tmem_base, const uint32_t full_bar, const uint32_t empty_bar) {
+  constexpr int G_LO = NLOAD - NG;
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {
+    uint32_t slot[NLOAD];
+#pragma unroll
+    for (int t = 0; t < NLOAD; ++t) {
+      int sidx = u + t;
+      uint32_t ph = phase;
+      if (sidx >= UNITS) {
+        sidx -= UNITS;
+        ph ^= 1u;
+      }
+      slot[t] = (uint32_t)sidx;
+      mbar_wait(full_bar + 8 * sidx, ph);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      const uint32_t tmem_d = tmem_base + gi * TN;
+#pragma unroll
+      for (int t = 0; t <= G_LO + gi; ++t) {
+        const uint64_t da = make_smem_desc(smem_base + slot[t] * UNIT_BYTES);
+        const uint64_t db = make_smem_desc(smem_base + slot[G_LO + gi - t] * UNIT_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K) >> 4);  // +32 B per k-step inside the swizzle row
+          umma_i8_2cta_pred(tmem_d, da + adv, db + adv, IDESC, (kb != 0 || t != 0 || ks != 0) ? 1u : 0u);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NLOAD; ++t)  // units free (in both CTAs) once these MMAs retire
+      umma_commit_pair_pred(empty_bar + 8 * slot[t]);
+    u += NLOAD;
+    if (u >= UNITS) {
+      u -= UNITS;
+      phase ^= 1u;
+    }
+  }
 }
 
 struct OzParams {
@@ -180,7 +275,7 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t tempty_bar = tfull_bar + 8;          // accumulators drained (leader: 2 x EPI_WARPS arrivals)
   const uint32_t tmem_slot = tempty_bar + 8;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   uint32_t cta_rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -211,10 +306,11 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; warp-uniform loops, one elected lane issues) ==========
+    {
       int u = 0;
       uint32_t phase = 0;
       unsigned int wave_target = 0;
@@ -229,12 +325,15 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const unsigned int wave_pairs = (unsigned int)min(num_pairs, num_tiles - wave * num_pairs);
         auto align = [&]() {
           wave_target += wave_pairs;
-          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_counter) : "memory");
-          unsigned int seen;
-          do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_counter) : "memory");
-            if ((int)(seen - wave_target) < 0) __nanosleep(200);
-          } while ((int)(seen - wave_target) < 0);
+          if (lane == 0) {
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.wave_counter) : "memory");
+            unsigned int seen;
+            do {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wave_counter) : "memory");
+              if ((int)(seen - wave_target) < 0) __nanosleep(200);
+            } while ((int)(seen - wave_target) < 0);
+          }
+          __syncwarp();
         };
         if (leader && tile != pair && p.align_mode >= 1) align();
         int tm, tn;
@@ -248,10 +347,10 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int t = 0; t < nload; ++t) {
               mbar_wait(empty_bar + 8 * u, phase ^ 1);
               const uint32_t fb_leader = map_to_cta(full_bar + 8 * u, 0);
-              if (leader) mbar_expect_tx(full_bar + 8 * u, 2 * UNIT_BYTES);  // own + peer's A_t and B_t tiles
+              if (leader) mbar_expect_tx_elect(full_bar + 8 * u, 2 * UNIT_BYTES);  // own + peer's A_t and B_t tiles
               const uint32_t dst = smem_base + u * UNIT_BYTES;
-              tma_load_3d(dst, &map_a, fb_leader, kb * BK, row0, t);
-              tma_load_3d(dst + TILE_BYTES, &map_b, fb_leader, kb * BK, col0, t);
+              tma_load_3d_elect(dst, &map_a, fb_leader, kb * BK, row0, t);
+              tma_load_3d_elect(dst + TILE_BYTES, &map_b, fb_leader, kb * BK, col0, t);
               if (++u == UNITS) {
                 u = 0;
                 phase ^= 1;
@@ -262,55 +361,27 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loops, lane 0 issues) =====================
+    if (leader) {
       int u = 0;
       uint32_t phase = 0;
       uint32_t tphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         for (int ps = npass - 1; ps >= 0; --ps) {
           const int nload = min(p.nsl, 2 * ps + 2);
-          const int g_lo = 2 * ps;
-          const int ngroups = min(2, p.nsl - g_lo);
+          const int ngroups = min(2, p.nsl - 2 * ps);
           mbar_wait(tempty_bar, tphase ^ 1);  // both CTAs' epilogue warps drained the previous pass
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            int uu[MCD_OZAKI_MAX_SLICES];
-            {
-              int u2 = u;
-              uint32_t ph2 = phase;
-              for (int t = 0; t < nload; ++t) {
-                mbar_wait(full_bar + 8 * u2, ph2);
-                uu[t] = u2;
-                if (++u2 == UNITS) {
-                  u2 = 0;
-                  ph2 ^= 1;
-                }
-              }
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int gi = 0; gi < ngroups; ++gi) {
-              const int g = g_lo + gi;
-              const uint32_t tmem_d = tmem_base + gi * TN;
-              for (int t = 0; t <= g; ++t) {
-                const uint64_t da = make_smem_desc(smem_base + uu[t] * UNIT_BYTES);
-                const uint64_t db = make_smem_desc(smem_base + uu[g - t] * UNIT_BYTES + TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                  const uint64_t adv = (uint64_t)((ks * UMMA_K) >> 4);  // +32 B per k-step inside the swizzle row
-                  umma_i8_2cta(tmem_d, da + adv, db + adv, IDESC, (kb != 0 || t != 0 || ks != 0) ? 1u : 0u);
-                }
-              }
-            }
-            for (int t = 0; t < nload; ++t) {  // units free (in both CTAs) once these MMAs retire
-              umma_commit_pair(empty_bar + 8 * u);
-              if (++u == UNITS) {
-                u = 0;
-                phase ^= 1;
-              }
-            }
+          switch (nload * 2 + ngroups) {  // groups 2ps (and 2ps+1) from the slices 0 .. nload-1
+            case 2 * 2 + 2: mma_pass<2, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            case 4 * 2 + 2: mma_pass<4, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            case 6 * 2 + 2: mma_pass<6, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            case 8 * 2 + 2: mma_pass<8, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            case 3 * 2 + 1: mma_pass<3, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            case 5 * 2 + 1: mma_pass<5, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+            default: mma_pass<7, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
           }
-          umma_commit_pair(tfull_bar);  // both accumulators of this pass complete
+          umma_commit_pair_pred(tfull_bar);  // both accumulators of this pass complete
           tphase ^= 1;
         }
       }
