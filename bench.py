@@ -46,10 +46,10 @@ INT8_NOMINAL_TOPS = 4500.0  # B200 datasheet dense int8; the measured stand-in i
 
 def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-    capture of `scripts/profile_pass.py C5` (profiles/r01_C5_final_ncu_summary.json).  Valid for the C5 workload."""
-    p = os.path.join(ROOT, "profiles", "r01_C5_ozaki_ncu_summary.json")
-    if not os.path.exists(p):
-        p = os.path.join(ROOT, "profiles", "r01_C5_final_ncu_summary.json")
+    capture of `scripts/profile_pass.py C5` (newest profiles/r01_C5_*_ncu_summary.json).  Valid for the C5 workload."""
+    p = next((q for q in (os.path.join(ROOT, "profiles", n) for n in (
+        "r01_C5_v5_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json", "r01_C5_final_ncu_summary.json"))
+        if os.path.exists(q)), "")
     out = {}
     if not os.path.exists(p):
         return out
@@ -417,8 +417,9 @@ def main():
         }
         if args.workload == "C5":
             tr = load_traffic()
-            if "standardize_rows" in tr:  # RNA operand launch (the larger of the two)
-                rooflines["standardize"]["traffic"] = max(tr["standardize_rows"])
+            k1 = "standardize_digits" if (args.precision == "ozaki" and "standardize_digits" in tr) else "standardize_rows"
+            if k1 in tr:  # RNA operand launch (the larger of the two)
+                rooflines["standardize"]["traffic"] = max(tr[k1])
             if corr_kernel in tr:
                 rooflines["corr"]["traffic"] = tr[corr_kernel][0]
             if "lap_auction_kernel" in tr:
@@ -427,7 +428,7 @@ def main():
                                                     "counters for the step-1 launch and the cluster kernels")
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
-        roof["kernel"] = {"standardize": "standardize_rows", "corr": corr_kernel,
+        roof["kernel"] = {"standardize": "standardize_digits / standardize_rows", "corr": corr_kernel,
                           "lap": "lap_auction_kernel + lap_tail_mh_kernel / lap_tail_cluster_kernel (assignment "
                                  "solver, all steps)"}[dominant]
         roof["algorithmic_bytes"] = {"standardize": std_bytes, "corr": None, "lap": lap_bytes_alg}[dominant]

@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "mcd_internal.cuh"
 
@@ -201,49 +202,195 @@ __device__ __forceinline__ void decode_tile(int t, int tiles_m, int tiles_n, int
   tm = band * BAND_M + (rem - tn * hb);
 }
 
-// One pass of the MMA issuer over all k-blocks: NLOAD digit-slice units per k-block, NG significance groups
-// (g_lo = NLOAD - NG and, when NG = 2, g_lo + 1), fully unrolled -- the slot of every unit is a register.
-template <int NLOAD, int NG>
-__device__ __forceinline__ void mma_pass(const int num_kb, int& u, uint32_t& phase, const uint32_t smem_base,
-                                         const uint32_t tmem_base, const uint32_t full_bar, const uint32_t empty_bar) {
-  constexpr int G_LO = NLOAD - NG;
-#pragma unroll 1
-  for (int kb = 0; kb < num_kb; ++kb) {
-    uint32_t slot[NLOAD];
-#pragma unroll
-    for (int t = 0; t < NLOAD; ++t) {
-      int sidx = u + t;
-      uint32_t ph = phase;
-      if (sidx >= UNITS) {
-        sidx -= UNITS;
-        ph ^= 1u;
+// Order in which one pass loads the digit-slice units of a k-block, and the MMA schedule that goes with it.
+// A pass accumulates the significance groups g_lo = nload - ng (and g_lo + 1 when ng = 2) from the units
+// 0 .. nload-1; group g is the sum of the products (A unit t) x (B unit g - t).
+//   mode 0: units in index order, the whole k-block is waited for, multiplied group by group and freed together.
+//   mode 1: units walked from both ends (step a brings a, gh - a and, with two groups, gh - a - 1): every product is
+//           issued at the first step that has both its units and a unit goes back to the producer as soon as its
+//           last product is issued, while the rest of the k-block is still being multiplied -- the 12-unit ring
+//           then covers ~1.7 k-blocks of load latency in the heaviest pass (6 units per k-block) instead of 1.
+// Evaluated at compile time: the issuer is fully unrolled per (nload, ng, mode).
+struct PassPlan {
+  int nunits = 0, nsteps = 0, nprod = 0;
+  int ord[8] = {};  // load order: ord[k] = unit id
+  int pos[8] = {};  // inverse
+  unsigned wait_mask[8] = {};  // per step: units that must have landed (not waited for before)
+  unsigned free_mask[8] = {};  // per step: units whose last product was issued in this step
+  int step_end[8] = {};        // per step: end index into prod_*
+  int prod_a[16] = {}, prod_b[16] = {}, prod_g[16] = {};  // products: A unit, B unit, accumulator (0 / 1)
+  int prod_first[16] = {};                                // first product of its accumulator in the k-block
+};
+
+__host__ __device__ constexpr PassPlan make_pass_plan(int nload, int ng, int mode) {
+  PassPlan pl;
+  const int gh = nload - 1;
+  const int gl = nload - ng;
+  const bool two = ng == 2;
+  pl.nunits = nload;
+  unsigned seen = 0;
+  int n = 0;
+  for (int a = 0; a <= gh; ++a) {
+    const int cand[3] = {a, mode ? gh - a : -1, (mode && two) ? gh - a - 1 : -1};
+    for (int c = 0; c < 3; ++c) {
+      const int x = cand[c];
+      if (x >= 0 && x <= gh && !((seen >> x) & 1u)) {
+        seen |= 1u << x;
+        pl.pos[x] = n;
+        pl.ord[n++] = x;
       }
-      slot[t] = (uint32_t)sidx;
-      mbar_wait(full_bar + 8 * sidx, ph);
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int gi = 0; gi < NG; ++gi) {
-      const uint32_t tmem_d = tmem_base + gi * TN;
-#pragma unroll
-      for (int t = 0; t <= G_LO + gi; ++t) {
-        const uint64_t da = make_smem_desc(smem_base + slot[t] * UNIT_BYTES);
-        const uint64_t db = make_smem_desc(smem_base + slot[G_LO + gi - t] * UNIT_BYTES + TILE_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t adv = (uint64_t)((ks * UMMA_K) >> 4);  // +32 B per k-step inside the swizzle row
-          umma_i8_2cta_pred(tmem_d, da + adv, db + adv, IDESC, (kb != 0 || t != 0 || ks != 0) ? 1u : 0u);
+  }
+  unsigned have = 0, freed = 0, started = 0;
+  unsigned done[2] = {0, 0};
+  int np = 0, ns = 0;
+  const int total = (gh + 1) + (two ? gl + 1 : 0);
+  for (int a = 0; a <= gh && np < total; ++a) {
+    unsigned set = have;
+    for (int x = 0; x <= gh; ++x)
+      if (mode == 0 || x <= a || x >= gh - a - (two ? 1 : 0)) set |= 1u << x;
+    pl.wait_mask[ns] = set & ~have;
+    have = set;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int g = gl + gi;
+      for (int t = 0; t <= g; ++t) {
+        if (!((done[gi] >> t) & 1u) && ((have >> t) & 1u) && ((have >> (g - t)) & 1u)) {
+          done[gi] |= 1u << t;
+          pl.prod_a[np] = t;
+          pl.prod_b[np] = g - t;
+          pl.prod_g[np] = gi;
+          pl.prod_first[np] = ((started >> gi) & 1u) ? 0 : 1;
+          started |= 1u << gi;
+          ++np;
         }
       }
     }
+    unsigned fm = 0;  // a unit is finished once every product it takes part in has been issued
+    for (int x = 0; x <= gh; ++x) {
+      if ((freed >> x) & 1u) continue;
+      bool fin = true;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int g = gl + gi;
+        if (g - x >= 0) {
+          if (!((done[gi] >> x) & 1u)) fin = false;        // product (x, g - x)
+          if (!((done[gi] >> (g - x)) & 1u)) fin = false;  // product (g - x, x)
+        }
+      }
+      if (fin) fm |= 1u << x;
+    }
+    freed |= fm;
+    pl.free_mask[ns] = fm;
+    pl.step_end[ns] = np;
+    ++ns;
+  }
+  pl.nsteps = ns;
+  pl.nprod = np;
+  return pl;
+}
+
+template <int NLOAD, int NG, int MODE>
+__host__ __device__ constexpr uint32_t packed_load_order() {
+  constexpr PassPlan pl = make_pass_plan(NLOAD, NG, MODE);
+  uint32_t r = 0;
+  for (int k = 0; k < NLOAD; ++k) r |= (uint32_t)pl.ord[k] << (4 * k);
+  return r;
+}
+// nibble k = the unit loaded k-th in a k-block of this pass (the producer's view of the plan)
+__device__ __forceinline__ uint32_t load_order(int nload, int ng, int mode) {
+  if (mode == 0) return 0x76543210u;
+  switch (nload * 2 + ng) {
+    case 2 * 2 + 2: { constexpr uint32_t o = packed_load_order<2, 2, 1>(); return o; }
+    case 4 * 2 + 2: { constexpr uint32_t o = packed_load_order<4, 2, 1>(); return o; }
+    case 6 * 2 + 2: { constexpr uint32_t o = packed_load_order<6, 2, 1>(); return o; }
+    case 8 * 2 + 2: { constexpr uint32_t o = packed_load_order<8, 2, 1>(); return o; }
+    case 3 * 2 + 1: { constexpr uint32_t o = packed_load_order<3, 1, 1>(); return o; }
+    case 5 * 2 + 1: { constexpr uint32_t o = packed_load_order<5, 1, 1>(); return o; }
+    default: { constexpr uint32_t o = packed_load_order<7, 1, 1>(); return o; }
+  }
+}
+
+template <int NLOAD, int NG, int MODE>
+struct PlanOf {
+  static constexpr PassPlan pl = make_pass_plan(NLOAD, NG, MODE);
+};
+// compile-time loop: every index into the plan is a constant expression (a run-time index would force the plan
+// into local memory)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+// One pass of the MMA issuer over all k-blocks, fully unrolled -- the ring slot of every unit is a register.
+template <int NLOAD, int NG, int MODE>
+__device__ __forceinline__ void mma_pass(const int num_kb, int& u, uint32_t& phase, const uint32_t smem_base,
+                                         const uint32_t tmem_base, const uint32_t full_bar, const uint32_t empty_bar) {
+  using P = PlanOf<NLOAD, NG, MODE>;
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {
+    uint32_t slot[NLOAD], ph[NLOAD];  // unit x of this k-block was loaded pos[x]-th after slot u
+    static_for<0, NLOAD>([&](auto X) {
+      constexpr int x = decltype(X)::value;
+      constexpr int pos = P::pl.pos[x];
+      int sidx = u + pos;
+      ph[x] = phase;
+      if (sidx >= UNITS) {
+        sidx -= UNITS;
+        ph[x] ^= 1u;
+      }
+      slot[x] = (uint32_t)sidx;
+    });
+    static_for<0, P::pl.nsteps>([&](auto ST) {
+      constexpr int st = decltype(ST)::value;
+      static_for<0, NLOAD>([&](auto X) {
+        constexpr int x = decltype(X)::value;
+        constexpr bool need = (P::pl.wait_mask[st] >> x) & 1u;
+        if constexpr (need) mbar_wait(full_bar + 8 * slot[x], ph[x]);
+      });
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr int p_begin = st == 0 ? 0 : P::pl.step_end[st == 0 ? 0 : st - 1];
+      constexpr int p_end = P::pl.step_end[st];
+      static_for<p_begin, p_end>([&](auto PI) {
+        constexpr int pi = decltype(PI)::value;
+        constexpr int ua = P::pl.prod_a[pi], ub = P::pl.prod_b[pi], gi = P::pl.prod_g[pi];
+        constexpr bool first = P::pl.prod_first[pi] != 0;
+        const uint32_t tmem_d = tmem_base + gi * TN;
+        const uint64_t da = make_smem_desc(smem_base + slot[ua] * UNIT_BYTES);
+        const uint64_t db = make_smem_desc(smem_base + slot[ub] * UNIT_BYTES + TILE_BYTES);
 #pragma unroll
-    for (int t = 0; t < NLOAD; ++t)  // units free (in both CTAs) once these MMAs retire
-      umma_commit_pair_pred(empty_bar + 8 * slot[t]);
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K) >> 4);  // +32 B per k-step inside the swizzle row
+          umma_i8_2cta_pred(tmem_d, da + adv, db + adv, IDESC, (kb != 0 || !first || ks != 0) ? 1u : 0u);
+        }
+      });
+      static_for<0, NLOAD>([&](auto X) {  // finished units go back to the producer (both CTAs) once the MMAs retire
+        constexpr int x = decltype(X)::value;
+        constexpr bool fin = (P::pl.free_mask[st] >> x) & 1u;
+        if constexpr (fin) umma_commit_pair_pred(empty_bar + 8 * slot[x]);
+      });
+    });
     u += NLOAD;
     if (u >= UNITS) {
       u -= UNITS;
       phase ^= 1u;
     }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void mma_pass_dispatch(int nload, int ngroups, const int num_kb, int& u, uint32_t& phase,
+                                                  const uint32_t smem_base, const uint32_t tmem_base,
+                                                  const uint32_t full_bar, const uint32_t empty_bar) {
+  switch (nload * 2 + ngroups) {  // groups 2ps (and 2ps+1) from the slices 0 .. nload-1
+    case 2 * 2 + 2: mma_pass<2, 2, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    case 4 * 2 + 2: mma_pass<4, 2, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    case 6 * 2 + 2: mma_pass<6, 2, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    case 8 * 2 + 2: mma_pass<8, 2, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    case 3 * 2 + 1: mma_pass<3, 1, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    case 5 * 2 + 1: mma_pass<5, 1, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
+    default: mma_pass<7, 1, MODE>(num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
   }
 }
 
@@ -262,6 +409,7 @@ struct OzParams {
   int64_t ldct;
   unsigned int* wave_counter;  // zeroed before the launch
   int align_mode;              // 0 free-running, 1 align the producers per wave, 2 per wave and pass
+  int plan_mode;               // PassPlan mode
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -343,8 +491,10 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int ps = npass - 1; ps >= 0; --ps) {
           const int nload = min(p.nsl, 2 * ps + 2);  // slices 0 .. nload-1 take part in the groups 2ps, 2ps+1
           if (leader && ps != npass - 1 && p.align_mode >= 2) align();  // also re-align at every pass
+          const uint32_t order = load_order(nload, min(2, p.nsl - 2 * ps), p.plan_mode);
           for (int kb = 0; kb < p.num_kb; ++kb) {
-            for (int t = 0; t < nload; ++t) {
+            for (int k = 0; k < nload; ++k) {
+              const int t = (int)((order >> (4 * k)) & 15u);  // units are loaded in the order the MMA plan needs them
               mbar_wait(empty_bar + 8 * u, phase ^ 1);
               const uint32_t fb_leader = map_to_cta(full_bar + 8 * u, 0);
               if (leader) mbar_expect_tx_elect(full_bar + 8 * u, 2 * UNIT_BYTES);  // own + peer's A_t and B_t tiles
@@ -372,15 +522,10 @@ corr_ozaki_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int ngroups = min(2, p.nsl - 2 * ps);
           mbar_wait(tempty_bar, tphase ^ 1);  // both CTAs' epilogue warps drained the previous pass
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          switch (nload * 2 + ngroups) {  // groups 2ps (and 2ps+1) from the slices 0 .. nload-1
-            case 2 * 2 + 2: mma_pass<2, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            case 4 * 2 + 2: mma_pass<4, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            case 6 * 2 + 2: mma_pass<6, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            case 8 * 2 + 2: mma_pass<8, 2>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            case 3 * 2 + 1: mma_pass<3, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            case 5 * 2 + 1: mma_pass<5, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-            default: mma_pass<7, 1>(p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar); break;
-          }
+          if (p.plan_mode == 0)
+            mma_pass_dispatch<0>(nload, ngroups, p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar);
+          else
+            mma_pass_dispatch<1>(nload, ngroups, p.num_kb, u, phase, smem_base, tmem_base, full_bar, empty_bar);
           umma_commit_pair_pred(tfull_bar);  // both accumulators of this pass complete
           tphase ^= 1;
         }
@@ -552,6 +697,8 @@ int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int
   {
     const char* e = getenv("MCD_OZAKI_ALIGN");
     p.align_mode = e ? atoi(e) : 1;
+    e = getenv("MCD_OZAKI_PLAN");
+    p.plan_mode = e ? atoi(e) : 1;
   }
   MCD_CUDA(h, cudaMemsetAsync(p.wave_counter, 0, sizeof(unsigned int), h->stream));
   MCD_CUDA(h, cudaFuncSetAttribute(corr_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

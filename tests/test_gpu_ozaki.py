@@ -70,6 +70,80 @@ def test_ozaki_digits_reconstruct_unit_rows(handle, nsl):
     assert (top >= 0.25 - 1e-9).all() and (top < 0.5).all()
 
 
+def _digits_of(handle, x_dev, ncells, G, ldx, nsl):
+    torch = _torch()
+    lib, h = handle.lib, handle.h
+    ldk = lib.mcd_padded_k_split(G)
+    a8 = torch.full((nsl, ncells, ldk), 55, dtype=torch.int8, device="cuda")
+    sa = torch.empty(ncells, dtype=torch.float64, device="cuda")
+    na = torch.empty(ncells, dtype=torch.float64, device="cuda")
+    handle.check(lib.mcd_standardize_ozaki(h, x_dev.data_ptr(), ncells, G, ldx, a8.data_ptr(), nsl, sa.data_ptr(),
+                                           na.data_ptr()))
+    handle.synchronize()
+    return a8.cpu().numpy(), sa.cpu().numpy(), na.cpu().numpy()
+
+
+@pytest.mark.parametrize("nsl", [6, 8])
+@pytest.mark.parametrize("G", [5, 130, 256, 1000, 3000, 4097, 8192, 9001, 13000, 16385, 20000, 24576])
+def test_digit_fast_path_every_launch_shape(handle, G, nsl):
+    """K1's digit fast path (4 consecutive genes per thread, 256-bit loads, fma rounding) in each of its launch
+    shapes, from aligned and from strided / unaligned input (scalar loads): digits reconstruct the unit rows to half
+    a unit of the last digit, padding is zero, and zero-variance rows are exactly zero whatever their constant
+    (sum/G need not reproduce the constant: log1p(2) at G = 3000 does not)."""
+    from oracle import restatement as R
+
+    torch = _torch()
+    rng = np.random.default_rng(G)
+    ncells = 9
+    x = np.log1p(rng.poisson(3.0, size=(ncells, G)).astype(np.float64)) + rng.random((ncells, G)) * 1e-3
+    x[2] = np.log1p(2.0)
+    x[5] = 1.0 / 3.0
+    x[7] = 0.1
+    xc, nrm = R.standardise(x)
+    flat = np.array([2, 5, 7])
+    nrm[flat] = 0.0  # the oracle's pairwise mean may leave rounding residue on a constant row; the kernel must not
+    xc[flat] = 0.0
+    unit = np.divide(xc, nrm[:, None], out=np.zeros_like(xc), where=nrm[:, None] > 0)
+    for ldx, off in ((G, 0), (G + 3, 1)):  # contiguous (vector loads when aligned) and strided + misaligned
+        buf = torch.zeros(ncells * ldx + 8, dtype=torch.float64, device="cuda")
+        view = buf[off:off + ncells * ldx].view(ncells, ldx)
+        view[:, :G] = torch.from_numpy(x).cuda()
+        a8, sa, na = _digits_of(handle, view, ncells, G, ldx, nsl)
+        assert a8.min() >= -64 and a8.max() <= 63
+        q = np.zeros(a8.shape[1:], dtype=np.float64)
+        for t in range(nsl):
+            q = q * 128.0 + a8[t].astype(np.float64)
+        rec = q[:, :G] * 2.0 ** -(7 * nsl - 1) * sa[:, None]
+        tol = 2.0 ** -(7 * nsl - 1) * sa.max()
+        assert np.abs(rec - unit).max() <= max(tol, 1e-15), (G, nsl, ldx)  # FP64 rounding of the oracle itself
+        assert (a8[:, :, G:] == 0).all()
+        assert (a8[:, flat, :] == 0).all()
+        assert (na[flat] == 0).all()
+        assert np.abs(na - nrm).max() <= 1e-12 * nrm.max()
+
+
+def test_digit_fast_path_matches_generic_kernel(handle, monkeypatch):
+    """Same rows through the fast digit kernel and the generic one (MCD_K1_GENERIC=1): identical scales, and digit
+    vectors that differ by at most one unit of the last digit (the fast path rounds c*mul once, in an fma)."""
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    G, ncells, nsl = 5000, 64, 6
+    x = torch.from_numpy(np.log1p(rng.poisson(2.0, size=(ncells, G)).astype(np.float64))).cuda()
+    a_fast, s_fast, n_fast = _digits_of(handle, x, ncells, G, G, nsl)
+    monkeypatch.setenv("MCD_K1_GENERIC", "1")
+    a_gen, s_gen, n_gen = _digits_of(handle, x, ncells, G, G, nsl)
+    monkeypatch.delenv("MCD_K1_GENERIC")
+    assert (s_fast == s_gen).all()
+    assert np.abs(n_fast - n_gen).max() <= 1e-13 * n_gen.max()
+    qf = np.zeros(a_fast.shape[1:])
+    qg = np.zeros(a_gen.shape[1:])
+    for t in range(nsl):
+        qf = qf * 128.0 + a_fast[t]
+        qg = qg * 128.0 + a_gen[t]
+    # different summation order of the mean -> the centred values differ by ~1e-16 relative -> a few last-digit units
+    assert np.abs(qf - qg).max() <= 8.0
+
+
 @pytest.mark.parametrize("shape", [(4, 4, 6), (128, 256, 64), (130, 257, 100), (300, 200, 1000), (515, 700, 4099),
                                    (1000, 249, 20000)])
 def test_corr_ozaki_kernel(handle, shape):
