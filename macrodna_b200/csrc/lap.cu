@@ -673,6 +673,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
   __shared__ int cand_j[LAP_THREADS * CAND_T];
   __shared__ double red[LAP_WARPS];
   __shared__ Top2 wred[LAP_WARPS];
+  __shared__ int s_last;  // this CTA finished the last chunk of a split row
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -778,22 +779,35 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
             s.pbound[item] = cb;
             int prev;  // release: partials and list slots above are visible before the count
             asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[kk]) : "memory");
-            if (prev == nch - 1) {
-              Top2 a{NEG_INF, NEG_INF, -1, -1};
-              double bound = NEG_INF;
-              for (int cc = 0; cc < nch; ++cc) {
-                const int sl = f * nch + cc;
-                Top2 b{__ldcg(&s.pv1[sl]), __ldcg(&s.pv2[sl]), __ldcg(&s.pj1[sl]), __ldcg(&s.pj2[sl])};
-                if (b.j1 >= 0) top2_push(a, b.v1, b.j1);
-                if (b.j2 >= 0) top2_push(a, b.v2, b.j2);
-                bound = fmax(bound, __ldcg(&s.pbound[sl]));
-              }
+            s_last = (prev == nch - 1) ? 1 : 0;
+            if (c == 0) sweeps++;
+          }
+          __syncthreads();
+          // The CTA that finished the row's last chunk merges the chunk tops: one lane per chunk, so the merge is
+          // ONE L2 latency + a warp reduction (a single thread walking the nch partials paid nch dependent L2
+          // latencies, ~11 us at 16 chunks, on the critical path of every wide round).
+          if (s_last && warp == 0) {
+            Top2 b{NEG_INF, NEG_INF, -1, -1};
+            double bound = NEG_INF;
+            if (lane < nch) {
+              const int sl = f * nch + lane;
+              b.v1 = __ldcg(&s.pv1[sl]);
+              b.v2 = __ldcg(&s.pv2[sl]);
+              b.j1 = __ldcg(&s.pj1[sl]);
+              b.j2 = __ldcg(&s.pj2[sl]);
+              bound = __ldcg(&s.pbound[sl]);
+              if (b.j1 < 0) b.v1 = NEG_INF;
+              if (b.j2 < 0) b.v2 = NEG_INF;
+            }
+            const Top2 a = top2_warp_reduce(b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+            if (lane == 0) {
               s.done[kk] = 0;
               s.lbound[i] = bound;
               s.lvalid[i] = 1;
               wide_finalize_bid(s, kk, i, a, eps);
             }
-            if (c == 0) sweeps++;
           }
           __syncthreads();
         }
@@ -865,13 +879,20 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
             s.pj2[slot] = t.j2;
             int prev;  // release: the partial above is visible before the count; no L1-invalidating fence
             asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[k]) : "memory");
-            if (prev == nch - 1) {
-              Top2 a{NEG_INF, NEG_INF, -1, -1};
-              for (int cc = 0; cc < nch; ++cc) {
-                const int64_t sl = (int64_t)k * nch + cc;
-                Top2 b{__ldcg(&s.pv1[sl]), __ldcg(&s.pv2[sl]), __ldcg(&s.pj1[sl]), __ldcg(&s.pj2[sl])};
-                top2_merge(a, b);
-              }
+            s_last = (prev == nch - 1) ? 1 : 0;
+          }
+        }
+        if (nch > 1) {  // uniform.  Last CTA of the row: lanes of warp 0 fetch the partials in parallel (see above)
+          __syncthreads();
+          if (s_last && warp == 0) {
+            Top2 a{NEG_INF, NEG_INF, -1, -1};
+            for (int cc = lane; cc < nch; cc += 32) {
+              const int64_t sl = (int64_t)k * nch + cc;
+              Top2 b{__ldcg(&s.pv1[sl]), __ldcg(&s.pv2[sl]), __ldcg(&s.pj1[sl]), __ldcg(&s.pj2[sl])};
+              top2_merge(a, b);
+            }
+            a = top2_warp_reduce(a);
+            if (lane == 0) {
               s.done[k] = 0;
               wide_finalize_bid(s, k, i, a, eps);
             }
