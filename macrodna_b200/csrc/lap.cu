@@ -721,95 +721,26 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     }
     const long long t0 = clock64();
     const int* un = s.un[cur];
-    if (use_lists && nu >= list_min_nu) {
-      // ---- bidding, stage 1: one warp per bidder from its candidate list; failures go to a global list
+    const bool lists_round = use_lists && nu >= list_min_nu;
+    if (lists_round) {
+      // ---- bidding from the candidate lists, one warp per bidder.  A bidder whose list cannot certify its top-2
+      //      sits this round out (bj = -1, re-queued by the resolution below) while its list is rebuilt next to
+      //      the resolution, behind the SAME grid barrier -- a Jacobi auction may let any subset of the unassigned
+      //      persons bid, and a list built from prices that are still rising stays valid: every price it read is <=
+      //      the final one, so every unlisted object is still below the bound.  (The rebuild used to be a stage of
+      //      its own between two barriers, followed by the failed bidders' bids: ~8 us of every wide round.)
       for (int k = (blockIdx.x * LAP_WARPS + warp); k < nu; k += gridDim.x * LAP_WARPS) {
         const int i = ldm(&un[k]);
         bool ok = false;
         Top2 t;
         ok = list_bid<true>(s, i, lane, t);
         if (lane == 0) {
-          if (ok)
+          if (ok) {
             wide_finalize_bid(s, k, i, t, eps);
-          else
-            s.fail[atomicAdd(&ctrl->nfail[parity], 1)] = k;
-        }
-      }
-      grid.sync();
-      // ---- stage 2: failed lists are rebuilt by row sweeps.  With at least a grid-full of failures one CTA
-      //      sweeps one row; with fewer, every row is split over nch CTAs (chunk_scan_build) so that a round
-      //      costs one memory latency instead of one CTA streaming a whole row by itself.
-      const int nfail = ldm(&ctrl->nfail[parity]);
-      if (gtid == 0) ctrl->nfail[parity ^ 1] = 0;
-      // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
-      // chunks at >= 1024 objects and the partial slots within their arrays
-      int nch = 1;
-      if (nfail > 0 && s.list_k == LIST_K) {
-        const int item_cap = (int)gridDim.x * s.chunk_waves;
-        while (nch < 16 && 2 * nch * nfail <= item_cap && 2 * nch * nfail <= MAX_GRID_SLOTS && s.m / (2 * nch) >= 1024)
-          nch *= 2;
-      }
-      if (nch == 1) {
-        for (int f = blockIdx.x; f < nfail; f += gridDim.x) {
-          const int kk = ldm(&s.fail[f]);
-          const int i = ldm(&un[kk]);
-          const Top2 t = full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
-          if (tid == 0) {
-            wide_finalize_bid(s, kk, i, t, eps);
-            sweeps++;
+          } else {
+            s.bj[k] = -1;
+            s.fail[atomicAdd(&ctrl->nfail[parity], 1)] = i;
           }
-        }
-      } else {
-        const int kc = LIST_K / nch;
-        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
-        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-          const int f = item / nch, c = item - f * nch;
-          const int kk = ldm(&s.fail[f]);
-          const int i = ldm(&un[kk]);
-          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
-          double cb;
-          const Top2 t = kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
-                                  : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
-          if (tid == 0) {
-            s.pv1[item] = t.v1;
-            s.pv2[item] = t.v2;
-            s.pj1[item] = t.j1;
-            s.pj2[item] = t.j2;
-            s.pbound[item] = cb;
-            int prev;  // release: partials and list slots above are visible before the count
-            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[kk]) : "memory");
-            s_last = (prev == nch - 1) ? 1 : 0;
-            if (c == 0) sweeps++;
-          }
-          __syncthreads();
-          // The CTA that finished the row's last chunk merges the chunk tops: one lane per chunk, so the merge is
-          // ONE L2 latency + a warp reduction (a single thread walking the nch partials paid nch dependent L2
-          // latencies, ~11 us at 16 chunks, on the critical path of every wide round).
-          if (s_last && warp == 0) {
-            Top2 b{NEG_INF, NEG_INF, -1, -1};
-            double bound = NEG_INF;
-            if (lane < nch) {
-              const int sl = f * nch + lane;
-              b.v1 = __ldcg(&s.pv1[sl]);
-              b.v2 = __ldcg(&s.pv2[sl]);
-              b.j1 = __ldcg(&s.pj1[sl]);
-              b.j2 = __ldcg(&s.pj2[sl]);
-              bound = __ldcg(&s.pbound[sl]);
-              if (b.j1 < 0) b.v1 = NEG_INF;
-              if (b.j2 < 0) b.v2 = NEG_INF;
-            }
-            const Top2 a = top2_warp_reduce(b);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-            if (lane == 0) {
-              s.done[kk] = 0;
-              s.lbound[i] = bound;
-              s.lvalid[i] = 1;
-              wide_finalize_bid(s, kk, i, a, eps);
-            }
-          }
-          __syncthreads();
         }
       }
     } else {
@@ -905,11 +836,75 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     const long long t1 = clock64();
     grid.sync();
     const long long t2 = clock64();
+    if (lists_round) {
+      // ---- failed lists are rebuilt by row sweeps, concurrently with the resolution (which only the first
+      //      ceil(nu / 256) CTAs take part in: the rebuild items are dealt from the END of the grid).  With at
+      //      least a grid-full of failures one CTA sweeps one row; with fewer, every row is split over nch CTAs
+      //      (chunk_scan_*) so that a rebuild costs one memory latency instead of one CTA streaming a whole row.
+      const int nfail = ldm(&ctrl->nfail[parity]);
+      if (gtid == 0) {
+        ctrl->nfail[parity ^ 1] = 0;
+        if (nfail > 0) atomicAdd(&ctrl->progress[parity], nfail);  // a rebuilt list is progress (no false "stalled")
+      }
+      // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
+      // chunks at >= 1024 objects and the partial slots within their arrays
+      int nch = 1;
+      if (nfail > 0 && s.list_k == LIST_K) {
+        const int item_cap = (int)gridDim.x * s.chunk_waves;
+        while (nch < 16 && 2 * nch * nfail <= item_cap && 2 * nch * nfail <= MAX_GRID_SLOTS && s.m / (2 * nch) >= 1024)
+          nch *= 2;
+      }
+      const int rb = (int)gridDim.x - 1 - (int)blockIdx.x;  // reversed CTA index
+      if (nch == 1) {
+        for (int f = rb; f < nfail; f += gridDim.x) {
+          const int i = ldm(&s.fail[f]);
+          (void)full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
+          if (tid == 0) sweeps++;
+        }
+      } else {
+        const int kc = LIST_K / nch;
+        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
+        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
+        for (int item = rb; item < items; item += gridDim.x) {
+          const int f = item / nch, c = item - f * nch;
+          const int i = ldm(&s.fail[f]);
+          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
+          double cb;
+          (void)(kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
+                          : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb));
+          if (tid == 0) {
+            s.pbound[item] = cb;
+            int prev;  // release: the chunk bound and the list slots above are visible before the count
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[i]) : "memory");
+            s_last = (prev == nch - 1) ? 1 : 0;
+            if (c == 0) sweeps++;
+          }
+          __syncthreads();
+          // the CTA that finished the row's last chunk publishes the list: bound = max of the chunk bounds, fetched
+          // by one lane per chunk (one L2 latency, not nch dependent ones)
+          if (s_last && warp == 0) {
+            double bound = lane < nch ? __ldcg(&s.pbound[f * nch + lane]) : NEG_INF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+            if (lane == 0) {
+              s.done[i] = 0;
+              s.lbound[i] = bound;
+              s.lvalid[i] = 1;
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
     // ---- resolution: one thread per bidder; the winner of each object applies its bid
     int* nxt = s.un[cur ^ 1];
     for (int k = gtid; k < nu; k += gthreads) {
       const int i = ldm(&un[k]);
       const int j = ldm(&s.bj[k]);
+      if (j < 0) {  // sat the round out (list being rebuilt)
+        nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = i;
+        continue;
+      }
       const unsigned long long kj = ldm(&s.key[j]);
       bool requeue = true;
       if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
