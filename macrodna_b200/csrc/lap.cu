@@ -63,17 +63,26 @@ constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite corr
 struct GridBarrier {
   unsigned int* counter;
   unsigned int target;
-  __device__ __forceinline__ void sync() {
+  // split form: a CTA may arrive, do work nobody waits for before the NEXT barrier, and only then wait
+  __device__ __forceinline__ void arrive() {
     __syncthreads();
     if (threadIdx.x == 0) {
       target += gridDim.x;
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == 0) {
       unsigned int seen;
       do {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
       } while ((int)(seen - target) < 0);
     }
     __syncthreads();
+  }
+  __device__ __forceinline__ void sync() {
+    arrive();
+    wait();
   }
 };
 
@@ -93,6 +102,7 @@ struct LapCtrl {
   int in_tail;      // the wide kernel stopped with <= TAIL_NU bidders: the narrow kernel continues the phase
   double eps;       // eps of the phase in flight (handed from the wide kernel to the narrow kernel)
   int nfail[2];     // bidders whose candidate list failed this round (double buffered by round parity)
+  int nhold[2];     // bidders that sat the round out because their list is being rebuilt (same buffering)
   unsigned int barrier[MAX_PHASES];  // one GridBarrier counter per wide-kernel launch
 };
 
@@ -114,8 +124,8 @@ struct LapState {
   int* lj;                   // [n * LIST_K] candidate objects
   double* lw;                // [n * LIST_K] their costs W[i, j]
   double* lbound;            // [n] no unlisted object is worth more than this to person i
-  int* lvalid;               // [n] list built
-  int* fail;                 // [n] list slots whose candidate list could not certify the top-2 this round
+  int* lvalid;               // [n] 0 = never built, v >= 1 = usable from wide-kernel round v - 1 on
+  int* fail;                 // [2][n] persons whose candidate list could not certify the top-2 (per round parity)
   int max_chunks;            // no-list mode: upper bound on CTAs sharing one row
   int chunk_waves;           // list rebuilds: at most this many chunks per CTA per round
   int* done;                 // [n] chunks finished per list slot
@@ -696,7 +706,10 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     s.col4row[i] = -1;
     s.un[0][i] = i;
     s.done[i] = 0;
-    if (first_phase) s.lvalid[i] = 0;
+    if (first_phase)
+      s.lvalid[i] = 0;
+    else if (s.lvalid[i] != 0)
+      s.lvalid[i] = 1;  // round stamps of the previous launch (see the bidding stage) -> plain "valid"
   }
   if (gtid == 0) {
     ctrl->cnt[0] = s.n;
@@ -705,6 +718,8 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     ctrl->progress[1] = 0;
     ctrl->nfail[0] = 0;
     ctrl->nfail[1] = 0;
+    ctrl->nhold[0] = 0;
+    ctrl->nhold[1] = 0;
   }
   grid.sync();
   int cur = 0;
@@ -722,15 +737,29 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     const long long t0 = clock64();
     const int* un = s.un[cur];
     const bool lists_round = use_lists && nu >= list_min_nu;
+    const int rnd = (int)rounds;
+    int* const failp = s.fail + (size_t)parity * s.n;  // double buffered: a rebuild may still read last round's
     if (lists_round) {
       // ---- bidding from the candidate lists, one warp per bidder.  A bidder whose list cannot certify its top-2
-      //      sits this round out (bj = -1, re-queued by the resolution below) while its list is rebuilt next to
-      //      the resolution, behind the SAME grid barrier -- a Jacobi auction may let any subset of the unassigned
-      //      persons bid, and a list built from prices that are still rising stays valid: every price it read is <=
-      //      the final one, so every unlisted object is still below the bound.  (The rebuild used to be a stage of
-      //      its own between two barriers, followed by the failed bidders' bids: ~8 us of every wide round.)
+      //      sits out (bj = -1, re-queued by the resolution below) while its list is rebuilt OFF the round's critical
+      //      path: a Jacobi auction may let any subset of the unassigned persons bid, and a list built from prices
+      //      that are still rising stays valid (every price it read is <= the final one, so every unlisted object
+      //      is still below the bound).  lvalid[i] = v means "usable from round v - 1 on" (1 = always): the failing
+      //      warp stamps round + 2, the round by which an asynchronous chunked rebuild is certainly published
+      //      (its CTAs arrive at the NEXT round's first barrier only after publishing); a whole-row rebuild
+      //      (many failures, synchronous) resets the stamp to 1 before this round's second barrier.
+      //      (The rebuild used to be a stage of its own between two barriers, followed by the failed bidders' bids:
+      //      ~8 us of every wide round.)
       for (int k = (blockIdx.x * LAP_WARPS + warp); k < nu; k += gridDim.x * LAP_WARPS) {
         const int i = ldm(&un[k]);
+        const int lv = ldm(&s.lvalid[i]);
+        if (lv > rnd + 1) {  // list being rebuilt: hold
+          if (lane == 0) {
+            s.bj[k] = -1;
+            atomicAdd(&ctrl->nhold[parity], 1);  // a pending rebuild is progress (no false "stalled")
+          }
+          continue;
+        }
         bool ok = false;
         Top2 t;
         ok = list_bid<true>(s, i, lane, t);
@@ -739,7 +768,8 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
             wide_finalize_bid(s, k, i, t, eps);
           } else {
             s.bj[k] = -1;
-            s.fail[atomicAdd(&ctrl->nfail[parity], 1)] = i;
+            s.lvalid[i] = rnd + 3;
+            failp[atomicAdd(&ctrl->nfail[parity], 1)] = i;
           }
         }
       }
@@ -836,65 +866,20 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     const long long t1 = clock64();
     grid.sync();
     const long long t2 = clock64();
-    if (lists_round) {
-      // ---- failed lists are rebuilt by row sweeps, concurrently with the resolution (which only the first
-      //      ceil(nu / 256) CTAs take part in: the rebuild items are dealt from the END of the grid).  With at
-      //      least a grid-full of failures one CTA sweeps one row; with fewer, every row is split over nch CTAs
-      //      (chunk_scan_*) so that a rebuild costs one memory latency instead of one CTA streaming a whole row.
-      const int nfail = ldm(&ctrl->nfail[parity]);
-      if (gtid == 0) {
-        ctrl->nfail[parity ^ 1] = 0;
-        if (nfail > 0) atomicAdd(&ctrl->progress[parity], nfail);  // a rebuilt list is progress (no false "stalled")
-      }
-      // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
-      // chunks at >= 1024 objects and the partial slots within their arrays
-      int nch = 1;
-      if (nfail > 0 && s.list_k == LIST_K) {
-        const int item_cap = (int)gridDim.x * s.chunk_waves;
-        while (nch < 16 && 2 * nch * nfail <= item_cap && 2 * nch * nfail <= MAX_GRID_SLOTS && s.m / (2 * nch) >= 1024)
-          nch *= 2;
-      }
-      const int rb = (int)gridDim.x - 1 - (int)blockIdx.x;  // reversed CTA index
-      if (nch == 1) {
-        for (int f = rb; f < nfail; f += gridDim.x) {
-          const int i = ldm(&s.fail[f]);
-          (void)full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);
-          if (tid == 0) sweeps++;
-        }
-      } else {
-        const int kc = LIST_K / nch;
-        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
-        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
-        for (int item = rb; item < items; item += gridDim.x) {
-          const int f = item / nch, c = item - f * nch;
-          const int i = ldm(&s.fail[f]);
-          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
-          double cb;
-          (void)(kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
-                          : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb));
-          if (tid == 0) {
-            s.pbound[item] = cb;
-            int prev;  // release: the chunk bound and the list slots above are visible before the count
-            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[i]) : "memory");
-            s_last = (prev == nch - 1) ? 1 : 0;
-            if (c == 0) sweeps++;
-          }
-          __syncthreads();
-          // the CTA that finished the row's last chunk publishes the list: bound = max of the chunk bounds, fetched
-          // by one lane per chunk (one L2 latency, not nch dependent ones)
-          if (s_last && warp == 0) {
-            double bound = lane < nch ? __ldcg(&s.pbound[f * nch + lane]) : NEG_INF;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-            if (lane == 0) {
-              s.done[i] = 0;
-              s.lbound[i] = bound;
-              s.lvalid[i] = 1;
-            }
-          }
-          __syncthreads();
-        }
-      }
+    // failures of this round's bidding stage (0 in the rounds without lists)
+    const int nfail = lists_round ? ldm(&ctrl->nfail[parity]) : 0;
+    const int nhold = lists_round ? ldm(&ctrl->nhold[parity]) : 0;
+    if (lists_round && gtid == 0) {  // the other parity's counters are next touched behind this round's second barrier
+      ctrl->nfail[parity ^ 1] = 0;
+      ctrl->nhold[parity ^ 1] = 0;
+    }
+    // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
+    // chunks at >= 1024 objects and the partial slots within their arrays
+    int nch = 1;
+    if (nfail > 0 && s.list_k == LIST_K) {
+      const int item_cap = (int)gridDim.x * s.chunk_waves;
+      while (nch < 16 && 2 * nch * nfail <= item_cap && 2 * nch * nfail <= MAX_GRID_SLOTS && s.m / (2 * nch) >= 1024)
+        nch *= 2;
     }
     // ---- resolution: one thread per bidder; the winner of each object applies its bid
     int* nxt = s.un[cur ^ 1];
@@ -933,7 +918,65 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     rounds++;
     bids += nu;
     const long long t3 = clock64();
-    grid.sync();
+    if (lists_round && nfail > 0) {
+      // ---- failed lists are rebuilt by row sweeps.  With at least a grid-full of failures one CTA sweeps one row
+      //      (synchronous: done before this barrier).  With fewer, every row is split over nch CTAs (chunk_scan_*:
+      //      one memory latency instead of one CTA streaming a whole row) dealt from the END of the grid -- the
+      //      resolution above and the next round's bidding keep the first CTAs busy -- and those CTAs ARRIVE at
+      //      this barrier first and sweep afterwards: nobody waits for the rebuild before the next round's first
+      //      barrier, so it overlaps this barrier and the next bidding stage.
+      const int rb = (int)gridDim.x - 1 - (int)blockIdx.x;  // reversed CTA index
+      if (nch == 1) {
+        for (int f = rb; f < nfail; f += gridDim.x) {
+          const int i = ldm(&failp[f]);
+          (void)full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);  // also sets lvalid[i] = 1
+          if (tid == 0) sweeps++;
+        }
+        grid.sync();
+      } else {
+        // (with list_min_nu > 0 a later round may run without lists and reuse done[]: stay synchronous then -- the
+        // failed bidder merely holds one round longer than necessary)
+        const bool async_rebuild = list_min_nu == 0;
+        if (async_rebuild) grid.arrive();
+        const int kc = LIST_K / nch;
+        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
+        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
+        for (int item = rb; item < items; item += gridDim.x) {
+          const int f = item / nch, c = item - f * nch;
+          const int i = ldm(&failp[f]);
+          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
+          double cb;
+          (void)(kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
+                          : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb));
+          if (tid == 0) {
+            s.pbound[item] = cb;
+            int prev;  // release: the chunk bound and the list slots above are visible before the count
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[i]) : "memory");
+            s_last = (prev == nch - 1) ? 1 : 0;
+            if (c == 0) sweeps++;
+          }
+          __syncthreads();
+          // the CTA that finished the row's last chunk publishes the bound = max of the chunk bounds, fetched by one
+          // lane per chunk (one L2 latency, not nch dependent ones); lvalid already carries the round stamp
+          if (s_last && warp == 0) {
+            double bound = lane < nch ? __ldcg(&s.pbound[f * nch + lane]) : NEG_INF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+            if (lane == 0) {
+              s.done[i] = 0;
+              s.lbound[i] = bound;
+            }
+          }
+          __syncthreads();
+        }
+        if (async_rebuild)
+          grid.wait();
+        else
+          grid.sync();
+      }
+    } else {
+      grid.sync();
+    }
     const long long t4 = clock64();
     tph[0] += t1 - t0;
     tph[1] += t2 - t1;
@@ -948,7 +991,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     cur ^= 1;
     parity ^= 1;
     nu = nu_next;
-    if (prog == 0 && nu > 0) {
+    if (prog == 0 && nfail == 0 && nhold == 0 && nu > 0) {  // a requested / pending list rebuild is progress too
       stalled = true;
       break;
     }
@@ -2071,7 +2114,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up(n * LIST_K * 4, 256);   // lj
   b += align_up(n * LIST_K * 8, 256);   // lw
   b += align_up(n * 8, 256);            // lbound
-  b += 3 * align_up(n * 4, 256);        // lvalid, fail, done
+  b += 2 * align_up(n * 4, 256) + align_up(2 * n * 4, 256);  // lvalid, done, fail (x2)
   b += 3 * align_up(MAX_GRID_SLOTS * 8, 256) + 2 * align_up(MAX_GRID_SLOTS * 4, 256);  // split-row partials
   b += align_up(m * 8, 256);            // sp
   b += align_up(m * 4, 256);            // pred
@@ -2112,7 +2155,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.lw = reinterpret_cast<double*>(take(n * LIST_K * 8));
   s.lbound = reinterpret_cast<double*>(take(n * 8));
   s.lvalid = reinterpret_cast<int*>(take(n * 4));
-  s.fail = reinterpret_cast<int*>(take(n * 4));
+  s.fail = reinterpret_cast<int*>(take(2 * n * 4));  // double buffered by round parity
   s.done = reinterpret_cast<int*>(take(n * 4));
   s.pv1 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
   s.pv2 = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
