@@ -63,7 +63,8 @@ constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite corr
 struct GridBarrier {
   unsigned int* counter;
   unsigned int target;
-  // split form: a CTA may arrive, do work nobody waits for before the NEXT barrier, and only then wait
+  // split form: between arrive() and wait() a CTA may do work that nobody needs before the NEXT barrier (one
+  // outstanding barrier per CTA: the single monotonic counter cannot tell generations apart otherwise)
   __device__ __forceinline__ void arrive() {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -123,7 +124,9 @@ struct LapState {
   int* un[2];                // [n] bidder lists
   int* lj;                   // [n * LIST_K] candidate objects
   double* lw;                // [n * LIST_K] their costs W[i, j]
-  double* lbound;            // [n] no unlisted object is worth more than this to person i
+  double* lbound;            // [n] no unlisted object is worth more than this to person i -- stored as the
+                             //     order-preserving 64-bit key of the double (lb_store / lb_load): the chunks of a
+                             //     cooperative rebuild fold their bounds in with one atomic max each
   int* lvalid;               // [n] 0 = never built, v >= 1 = usable from wide-kernel round v - 1 on
   int* fail;                 // [2][n] persons whose candidate list could not certify the top-2 (per round parity)
   int max_chunks;            // no-list mode: upper bound on CTAs sharing one row
@@ -192,6 +195,11 @@ __device__ __forceinline__ double sortable_f64(unsigned long long k) {
   const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
   return __longlong_as_double((long long)b);
 }
+// candidate-list bound of person i (see LapState::lbound)
+__device__ __forceinline__ unsigned long long* lb_keys(const LapState& s) {
+  return reinterpret_cast<unsigned long long*>(s.lbound);
+}
+__device__ __forceinline__ void lb_store(const LapState& s, int i, double b) { lb_keys(s)[i] = f64_sortable(b); }
 // every lane returns the best key, its index, and the lane that held it
 __device__ __forceinline__ void warp_argmax_key(unsigned long long key, int j, unsigned long long& kbest, int& jbest,
                                                 int& wlane) {
@@ -241,7 +249,7 @@ __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top
   // everything that depends only on i is requested up front: the bid is two dependent memory latencies
   // (list, then the prices of its objects), not four
   const int valid = COHERENT ? ldm(&s.lvalid[i]) : s.lvalid[i];
-  const double b = COHERENT ? ldm(s.lbound + i) : s.lbound[i];
+  const double b = sortable_f64(COHERENT ? ldm(lb_keys(s) + i) : lb_keys(s)[i]);
   int js[LIST_K / 32];
   double ws[LIST_K / 32];
 #pragma unroll
@@ -276,7 +284,8 @@ __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top
 // list (top list_k by current value) with its bound.  Returns the top-2 in every thread.
 // smem: cand_v[NT*CAND_T] doubles, cand_j[NT*CAND_T] ints, red[NT/32] doubles.
 template <int NT, bool COHERENT>
-__device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* cand_j, double* red) {
+__device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* cand_j, double* red,
+                                bool set_valid = true) {
   constexpr int NC = NT * CAND_T;
   const int tid = threadIdx.x;
   const double* w = s.W + (int64_t)i * s.ldw;
@@ -370,8 +379,8 @@ __device__ Top2 full_scan_build(const LapState& s, int i, double* cand_v, int* c
     s.lw[(int64_t)i * LIST_K + q] = __ldg(w + j);
   }
   if (tid == 0) {
-    s.lbound[i] = bound;
-    s.lvalid[i] = 1;
+    lb_store(s, i, bound);
+    if (set_valid) s.lvalid[i] = 1;
   }
   Top2 t;
   t.v1 = cand_v[0];
@@ -729,25 +738,23 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
 
   // the exact (eps = 0) phase may hand its last aug_nu persons straight to the augmenting-path kernel
   const int stop_nu = (eps == 0.0 && aug_nu > tail_nu) ? aug_nu : tail_nu;
-  while (nu > stop_nu) {
+  for (;;) {
+    const long long t0 = clock64();
+    // (every list that was stamped "being rebuilt" has been rebuilt by the time the loop is left)
+    if (nu <= stop_nu || stalled) break;
     if (rounds >= s.max_rounds) {
       guard_hit = true;
       break;
     }
-    const long long t0 = clock64();
     const int* un = s.un[cur];
     const bool lists_round = use_lists && nu >= list_min_nu;
     const int rnd = (int)rounds;
-    int* const failp = s.fail + (size_t)parity * s.n;  // double buffered: a rebuild may still read last round's
+    int* const failp = s.fail + (size_t)parity * s.n;  // double buffered: the rebuild above reads last round's
     if (lists_round) {
       // ---- bidding from the candidate lists, one warp per bidder.  A bidder whose list cannot certify its top-2
-      //      sits out (bj = -1, re-queued by the resolution below) while its list is rebuilt OFF the round's critical
-      //      path: a Jacobi auction may let any subset of the unassigned persons bid, and a list built from prices
-      //      that are still rising stays valid (every price it read is <= the final one, so every unlisted object
-      //      is still below the bound).  lvalid[i] = v means "usable from round v - 1 on" (1 = always): the failing
-      //      warp stamps round + 2, the round by which an asynchronous chunked rebuild is certainly published
-      //      (its CTAs arrive at the NEXT round's first barrier only after publishing); a whole-row rebuild
-      //      (many failures, synchronous) resets the stamp to 1 before this round's second barrier.
+      //      sits out (bj = -1, re-queued by the resolution below) until its list has been rebuilt at the top of the
+      //      next round: a Jacobi auction may let any subset of the unassigned persons bid.  lvalid[i] = v means
+      //      "usable from round v - 1 on" (1 = always): the failing warp stamps round + 2.
       //      (The rebuild used to be a stage of its own between two barriers, followed by the failed bidders' bids:
       //      ~8 us of every wide round.)
       for (int k = (blockIdx.x * LAP_WARPS + warp); k < nu; k += gridDim.x * LAP_WARPS) {
@@ -769,6 +776,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
           } else {
             s.bj[k] = -1;
             s.lvalid[i] = rnd + 3;
+            lb_keys(s)[i] = 0ull;  // below every bound: the chunks of the rebuild fold theirs in by atomic max
             failp[atomicAdd(&ctrl->nfail[parity], 1)] = i;
           }
         }
@@ -873,6 +881,14 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       ctrl->nfail[parity ^ 1] = 0;
       ctrl->nhold[parity ^ 1] = 0;
     }
+    // ---- plan the rebuild of the failed lists.  It runs behind this round's SECOND barrier, next to the coming
+    //      round's bidding stage (the owners hold): between that barrier and the next first barrier no price changes,
+    //      so the rebuilt lists are deterministic, and the sweep shares a barrier interval with the bidding instead of
+    //      having one of its own.  With at least a grid-full of failures one CTA sweeps one row; with fewer, every row
+    //      is split over nch CTAs (chunk_scan_*: one memory latency instead of one CTA streaming a whole row), dealt
+    //      from the END of the grid -- bidder k is handled by CTA k / 8.  What does not depend on the prices is done
+    //      between the arrival at and the wait on the second barrier, off the critical path: the person of this
+    //      CTA's chunk is fetched and the chunk of its (immutable) cost row is pulled into L2.
     // chunks per failed row: up to 16 (kc = 8), as long as that keeps every CTA at <= ~2 chunks per round, the
     // chunks at >= 1024 objects and the partial slots within their arrays
     int nch = 1;
@@ -918,72 +934,56 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     rounds++;
     bids += nu;
     const long long t3 = clock64();
-    if (lists_round && nfail > 0) {
-      // ---- failed lists are rebuilt by row sweeps.  With at least a grid-full of failures one CTA sweeps one row
-      //      (synchronous: done before this barrier).  With fewer, every row is split over nch CTAs (chunk_scan_*:
-      //      one memory latency instead of one CTA streaming a whole row) dealt from the END of the grid -- the
-      //      resolution above and the next round's bidding keep the first CTAs busy -- and those CTAs ARRIVE at
-      //      this barrier first and sweep afterwards: nobody waits for the rebuild before the next round's first
-      //      barrier, so it overlaps this barrier and the next bidding stage.
-      const int rb = (int)gridDim.x - 1 - (int)blockIdx.x;  // reversed CTA index
+    grid.arrive();
+    const int rb = (int)gridDim.x - 1 - (int)blockIdx.x;  // reversed CTA index
+    const int rb_chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
+    int rb_i = -1;  // person whose chunk (item rb) this CTA sweeps after the second barrier
+    if (nch > 1 && rb < nfail * nch) {
+      rb_i = ldm(&failp[rb / nch]);
+      const int c = rb - (rb / nch) * nch;
+      const int j0 = min(s.m, c * rb_chunk), j1 = min(s.m, j0 + rb_chunk);
+      const char* row = reinterpret_cast<const char*>(s.W + (int64_t)rb_i * s.ldw);
+      for (int64_t off = ((int64_t)j0 * 8 & ~127ll) + (int64_t)tid * 128; off < (int64_t)j1 * 8; off += LAP_THREADS * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+    }
+    grid.wait();
+    // loop control of the coming round, requested before the sweep (their latency hides behind its loads)
+    const int nu_next = ldm(&ctrl->cnt[cur ^ 1]);
+    const int prog = ldm(&ctrl->progress[parity]);
+    if (nfail > 0) {
+      // ---- rebuild of the lists that failed in this round's bidding stage (planned above)
       if (nch == 1) {
         for (int f = rb; f < nfail; f += gridDim.x) {
           const int i = ldm(&failp[f]);
-          (void)full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red);  // also sets lvalid[i] = 1
+          (void)full_scan_build<LAP_THREADS, true>(s, i, cand_v, cand_j, red, false);  // lvalid keeps its stamp
           if (tid == 0) sweeps++;
         }
-        grid.sync();
       } else {
-        // (with list_min_nu > 0 a later round may run without lists and reuse done[]: stay synchronous then -- the
-        // failed bidder merely holds one round longer than necessary)
-        const bool async_rebuild = list_min_nu == 0;
-        if (async_rebuild) grid.arrive();
+        // nch * nfail <= grid * chunk_waves items: one chunk per CTA with the default chunk_waves = 1 (the first
+        // item's person was fetched before the barrier)
         const int kc = LIST_K / nch;
-        const int chunk = (((s.m + nch - 1) / nch) + 1) & ~1;
-        const int items = nfail * nch;  // <= MAX_GRID_SLOTS
+        const int items = nfail * nch;
         for (int item = rb; item < items; item += gridDim.x) {
           const int f = item / nch, c = item - f * nch;
-          const int i = ldm(&failp[f]);
-          const int j0 = min(s.m, c * chunk), j1 = min(s.m, j0 + chunk);
+          const int i = item == rb ? rb_i : ldm(&failp[f]);
+          const int j0 = min(s.m, c * rb_chunk), j1 = min(s.m, j0 + rb_chunk);
           double cb;
           (void)(kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
                           : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb));
+          // the chunk's bound goes into the person's bound by one atomic max (no counter, no publisher: the list
+          // is complete when every chunk CTA has passed the next barrier, which precedes the round it is stamped for)
           if (tid == 0) {
-            s.pbound[item] = cb;
-            int prev;  // release: the chunk bound and the list slots above are visible before the count
-            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&s.done[i]) : "memory");
-            s_last = (prev == nch - 1) ? 1 : 0;
+            atomicMax(lb_keys(s) + i, f64_sortable(cb));
             if (c == 0) sweeps++;
           }
-          __syncthreads();
-          // the CTA that finished the row's last chunk publishes the bound = max of the chunk bounds, fetched by one
-          // lane per chunk (one L2 latency, not nch dependent ones); lvalid already carries the round stamp
-          if (s_last && warp == 0) {
-            double bound = lane < nch ? __ldcg(&s.pbound[f * nch + lane]) : NEG_INF;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-            if (lane == 0) {
-              s.done[i] = 0;
-              s.lbound[i] = bound;
-            }
-          }
-          __syncthreads();
         }
-        if (async_rebuild)
-          grid.wait();
-        else
-          grid.sync();
       }
-    } else {
-      grid.sync();
     }
     const long long t4 = clock64();
     tph[0] += t1 - t0;
     tph[1] += t2 - t1;
     tph[2] += t3 - t2;
     tph[3] += t4 - t3;
-    const int nu_next = ldm(&ctrl->cnt[cur ^ 1]);
-    const int prog = ldm(&ctrl->progress[parity]);
     if (gtid == 0) {
       ctrl->cnt[cur] = 0;  // becomes the "next" list of the coming round
       ctrl->progress[parity ^ 1] = 0;
@@ -991,10 +991,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     cur ^= 1;
     parity ^= 1;
     nu = nu_next;
-    if (prog == 0 && nfail == 0 && nhold == 0 && nu > 0) {  // a requested / pending list rebuild is progress too
-      stalled = true;
-      break;
-    }
+    if (prog == 0 && nfail == 0 && nhold == 0 && nu > 0) stalled = true;  // (a requested / pending rebuild is progress)
   }
   if (gtid == 0) {
     ctrl->cur = cur;
@@ -1775,7 +1772,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
             s.lj[(int64_t)i * LIST_K + e] = e;
             s.lw[(int64_t)i * LIST_K + e] = s.W[(int64_t)i * s.ldw + e];
           }
-          if (tid == 0) s.lbound[i] = NEG_INF, s.lvalid[i] = 1;
+          if (tid == 0) lb_store(s, i, NEG_INF), s.lvalid[i] = 1;
           __syncthreads();
         } else {
           if (tid == 0) {
@@ -1795,7 +1792,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
           if (tid == 0) {
             double bound = NEG_INF;
             for (uint32_t c = 0; c < ncta; ++c) bound = fmax(bound, s_rbound[2 * c]);
-            s.lbound[i] = bound;
+            lb_store(s, i, bound);
             s.lvalid[i] = 1;
           }
           __syncthreads();  // list + bound visible to warp 0 below; s_reply may be overwritten by the next sweep

@@ -24,6 +24,6 @@ for st in settings:
     same = bool((a == ref[0]).all())
     print(json.dumps({"set": st, "ms_lap": round(d["ms_lap"], 2), "step_ms": [round(x, 2) for x in d["step_ms"]],
                       "rounds": d["step_rounds"], "bids": d["lap_bids"], "aug": [d["lap_aug_rows"], d["lap_aug_steps"]],
-                      "same_as_first": same, "cyc_per_round": [round(c / max(1, sum(d["step_rounds"]))) for c in d["lap_cycles"]], "ms_corr": round(d["ms_corr"], 2), "ms_standardize": round(d["ms_standardize"], 3)}), flush=True)
+                      "same_as_first": same, "obj_rel_diff": [float(abs(x - y) / abs(y)) for x, y in zip(o, ref[1])], "n_diff": int((a != ref[0]).sum()), "cyc_per_round": [round(c / max(1, sum(d["step_rounds"]))) for c in d["lap_cycles"]], "ms_corr": round(d["ms_corr"], 2), "ms_standardize": round(d["ms_standardize"], 3)}), flush=True)
     for k in st:
         del os.environ[k]
