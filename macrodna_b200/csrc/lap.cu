@@ -511,6 +511,117 @@ __device__ Top2 chunk_scan_select(const LapState& s, int i, int j0, int j1, int 
   return out;
 }
 
+// chunk_scan_select for 16 < kc <= 64 (few chunks per row: the rounds with many list failures), still without a
+// sort: every lane keeps its top-2 and the largest value it dropped, every warp hands its best KW = kc / 4 to the
+// CTA by KW arg-max rounds (NT/32 * KW = 2 kc candidates), and the chunk's kc are picked by RANK: candidate t counts
+// the candidates that beat it (2 kc shared-memory compares per thread, all threads in parallel) and, if fewer than
+// kc do, that count is its list slot.  Everything not passed on only raises the bound.  (chunk_scan_build's exact
+// top-kc costs a 55-stage bitonic sort of 1024 candidates: ~4 us of the ~10 us rebuild chain of a wide round.)
+// The chunk bound is returned in thread 0.
+template <int NT>
+__device__ void chunk_scan_rank(const LapState& s, int i, int j0, int j1, int c, int kc, double* s_cv, int* s_cj,
+                                double* s_wb, double* bound_out) {
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kw = kc / 4;        // 8 or 16 per warp
+  const int ncand = NW * kw;    // 2 * kc <= 128
+  const double* w = s.W + (int64_t)i * s.ldw;
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  double lb = NEG_INF;
+  auto push = [&](double v, int j) {
+    if (v > t.v1) {
+      lb = fmax(lb, t.v2);
+      t.v2 = t.v1, t.j2 = t.j1, t.v1 = v, t.j1 = j;
+    } else if (v > t.v2) {
+      lb = fmax(lb, t.v2);
+      t.v2 = v, t.j2 = j;
+    } else {
+      lb = fmax(lb, v);
+    }
+  };
+  if (s.vec) {  // j0 is even
+    constexpr int S = 2 * NT;
+    for (int j = j0 + 2 * tid; j < j1; j += 8 * S) {
+      double2 wv[8], pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j + u * S;
+        wv[u] = make_double2(NEG_INF, NEG_INF);
+        pv[u] = make_double2(0.0, 0.0);
+        if (jj + 1 < j1) {
+          wv[u] = __ldg(reinterpret_cast<const double2*>(w + jj));
+          pv[u] = ldm(reinterpret_cast<const double2*>(s.price + jj));
+        } else if (jj < j1) {
+          wv[u].x = __ldg(w + jj);
+          pv[u].x = ldm(s.price + jj);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j + u * S;
+        if (jj < j1) push(wv[u].x - pv[u].x, jj);
+        if (jj + 1 < j1) push(wv[u].y - pv[u].y, jj + 1);
+      }
+    }
+  } else {
+    for (int j = j0 + tid; j < j1; j += NT) push(__ldg(w + j) - ldm(s.price + j), j);
+  }
+  for (int r = 0; r < kw; ++r) {
+    double bv = t.v1;
+    int bj = t.j1;
+    warp_argmax(bv, bj);
+    if (bj >= 0 && bj == t.j1) {
+      t.v1 = t.v2, t.j1 = t.j2;
+      t.v2 = NEG_INF, t.j2 = -1;
+    }
+    if (lane == (r & 31)) {
+      s_cv[warp * kw + r] = bv;
+      s_cj[warp * kw + r] = bj;
+    }
+  }
+  double wb = fmax(lb, t.v1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wb = fmax(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+  if (lane == 0) s_wb[warp] = wb;
+  __syncthreads();
+  // rank of candidate tid among the ncand: order (value desc, object asc, slot asc) -- a strict total order even
+  // among the empty candidates (object -1, value NEG_INF)
+  double myv = NEG_INF;
+  int myj = -1, rank = 0x7fffffff;
+  if (tid < ncand) {
+    myv = s_cv[tid];
+    myj = s_cj[tid];
+    if (myj < 0) myv = NEG_INF;
+    rank = 0;
+    for (int u = 0; u < ncand; ++u) {
+      double uv = s_cv[u];
+      const int uj = s_cj[u];
+      if (uj < 0) uv = NEG_INF;
+      const bool before = (uv > myv) | ((uv == myv) & (((unsigned)uj < (unsigned)myj) | ((uj == myj) & (u < tid))));
+      rank += before ? 1 : 0;
+    }
+    if (rank < kc) {
+      s.lj[(int64_t)i * LIST_K + c * kc + rank] = myj >= 0 ? myj : (j0 < s.m ? j0 : 0);
+      s.lw[(int64_t)i * LIST_K + c * kc + rank] = myj >= 0 ? __ldg(w + myj) : NEG_INF;
+    }
+  }
+  // chunk bound: the warps' dropped values and the candidates that did not make the list
+  double cb = (tid < ncand && rank >= kc) ? myv : NEG_INF;
+  if (tid < NW) cb = fmax(cb, s_wb[tid]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cb = fmax(cb, __shfl_xor_sync(0xffffffffu, cb, o));
+  __syncthreads();  // every thread has read s_cv / s_cj / s_wb
+  if (lane == 0) s_wb[warp] = cb;
+  __syncthreads();
+  if (tid == 0) {
+    double b = NEG_INF;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) b = fmax(b, s_wb[q]);
+    *bound_out = b;
+  }
+  __syncthreads();  // scratch is free again
+}
+
 // One CHUNK [j0, j1) of a row sweep that rebuilds person i's candidate list cooperatively: nch CTAs each sweep
 // one chunk and contribute their chunk's top kc = list_k / nch objects to the list slots [c*kc, (c+1)*kc) plus a
 // chunk bound (no object of the chunk outside those kc is worth more).  The list is then the union of the chunk
@@ -683,7 +794,7 @@ __device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int 
 
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
                                                                   int tail_nu, int use_lists, int list_min_nu,
-                                                                  int aug_nu) {
+                                                                  int aug_nu, int rank_select) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || s.flags[0]) return;  // uniform: written only at the very end of earlier launches
   const int first_phase = phase_idx == 0;
@@ -967,9 +1078,13 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
           const int f = item / nch, c = item - f * nch;
           const int i = item == rb ? rb_i : ldm(&failp[f]);
           const int j0 = min(s.m, c * rb_chunk), j1 = min(s.m, j0 + rb_chunk);
-          double cb;
-          (void)(kc <= 16 ? chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb)
-                          : chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb));
+          double cb = NEG_INF;  // needed in thread 0
+          if (kc <= 16)
+            (void)chunk_scan_select<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
+          else if (rank_select)
+            chunk_scan_rank<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
+          else
+            (void)chunk_scan_build<LAP_THREADS>(s, i, j0, j1, c, kc, cand_v, cand_j, red, &cb);
           // the chunk's bound goes into the person's bound by one atomic max (no counter, no publisher: the list
           // is complete when every chunk CTA has passed the next barrier, which precedes the round it is stamped for)
           if (tid == 0) {
@@ -2261,7 +2376,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   if (n == m && (e = getenv("MCD_LAP_AUG_NU_SQUARE"))) aug_nu = atoi(e);
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
-    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu};
+    int rank_select = getenv("MCD_LAP_RANK_SELECT") ? atoi(getenv("MCD_LAP_RANK_SELECT")) : 1;
+    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                             h->stream));
     h->launches++;
