@@ -48,7 +48,7 @@ def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
     capture of `scripts/profile_pass.py C5` (newest profiles/r01_C5_*_ncu_summary.json).  Valid for the C5 workload."""
     p = next((q for q in (os.path.join(ROOT, "profiles", n) for n in (
-        "r01_C5_v5_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json", "r01_C5_final_ncu_summary.json"))
+        "r01_C5_v6_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json", "r01_C5_final_ncu_summary.json"))
         if os.path.exists(q)), "")
     out = {}
     if not os.path.exists(p):
