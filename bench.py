@@ -424,8 +424,8 @@ def main():
                 rooflines["corr"]["traffic"] = tr[corr_kernel][0]
             if "lap_auction_kernel" in tr:
                 rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
-                rooflines["lap"]["traffic_note"] = ("one wide-round launch (step 2) of lap_auction_kernel; ncu returned no DRAM "
-                                                    "counters for the step-1 launch and the cluster kernels")
+                rooflines["lap"]["traffic_note"] = ("the step-1 launch of lap_auction_kernel (wide rounds of the 10k x 50k step); "
+                                                    "ncu returns no DRAM counters for the cluster kernels of the narrow rounds")
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_digits / standardize_rows", "corr": corr_kernel,
