@@ -1011,18 +1011,21 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     // ---- resolution: one thread per bidder; the winner of each object applies its bid
     int* nxt = s.un[cur ^ 1];
     for (int k = gtid; k < nu; k += gthreads) {
+      // two dependent L2 latencies, not three: everything that depends only on k, then everything that depends on j
       const int i = ldm(&un[k]);
       const int j = ldm(&s.bj[k]);
+      const double gam = ldm(&s.gam[k]);
+      const double bval = ldm(&s.bval[k]);
       if (j < 0) {  // sat the round out (list being rebuilt)
         nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = i;
         continue;
       }
       const unsigned long long kj = ldm(&s.key[j]);
+      const double p_old = ldm(&s.price[j]);
+      const int prev = ldm(&s.owner[j]);
       bool requeue = true;
       if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
-        const double p_old = ldm(&s.price[j]);
-        const double p_new = p_old + ldm(&s.gam[k]);
-        const int prev = ldm(&s.owner[j]);
+        const double p_new = p_old + gam;
         if (prev < 0 || p_new > p_old) {
           if (prev >= 0) {
             s.col4row[prev] = -1;
@@ -1034,7 +1037,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
           // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
           // (bval + p_old) - p_new reproduces W - p_new to rounding, keeping the matched edge tight
           // at the 1-ulp level without re-reading W.
-          s.profit[i] = (ldm(&s.bval[k]) + p_old) - p_new;
+          s.profit[i] = (bval + p_old) - p_new;
           atomicAdd(&ctrl->progress[parity], 1);
           requeue = false;
         }
