@@ -121,6 +121,73 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
       : "memory");
 }
+// The producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes: stages, phases and descriptors live in
+// uniform registers) and only the instruction that must be issued once is predicated on elect.sync.  Inside an
+// `if (lane == 0)` region the compiler cannot prove the descriptors uniform and wraps every UTCHMMA / UTMALDG in an
+// ELECT / R2UR.BROADCAST waterfall loop (see corr_ozaki.cu, where this cost 16 % of the kernel).
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      "}\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                                     uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;\n"
+      "}\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   __syncwarp();  // .aligned: the whole warp must be converged here
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -177,7 +244,7 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   const uint32_t tempty_bar = tfull_bar + 8 * NUM_ACC;
   const uint32_t tmem_slot = tempty_bar + 8 * NUM_ACC;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   uint32_t cta_rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -211,10 +278,11 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_half = cta_rank * (A_SLICE_BYTES / 2);  // this CTA fetches rows [64*rank, 64*rank+64) of A
@@ -225,13 +293,13 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);  // 2 x 2 multicast A halves (own + peer's) + own B tiles
+          mbar_expect_tx_elect(fb, STAGE_BYTES);  // 2 x 2 multicast A halves (own + peer's) + own B tiles
           const uint32_t st = smem_base + stage * STAGE_BYTES;
-          tma_load_2d_mc(st + a_half, &map_a_hi, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2), (uint16_t)3);
-          tma_load_2d_mc(st + A_SLICE_BYTES + a_half, &map_a_lo, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2),
-                         (uint16_t)3);
-          tma_load_2d(st + 2 * A_SLICE_BYTES, &map_b_hi, fb, kb * BK, tn * BN);
-          tma_load_2d(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES, &map_b_lo, fb, kb * BK, tn * BN);
+          tma_load_2d_mc_elect(st + a_half, &map_a_hi, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2), (uint16_t)3);
+          tma_load_2d_mc_elect(st + A_SLICE_BYTES + a_half, &map_a_lo, fb, kb * BK, tm * BM + (int)cta_rank * (BM / 2),
+                               (uint16_t)3);
+          tma_load_2d_elect(st + 2 * A_SLICE_BYTES, &map_b_hi, fb, kb * BK, tn * BN);
+          tma_load_2d_elect(st + 2 * A_SLICE_BYTES + B_SLICE_BYTES, &map_b_lo, fb, kb * BK, tn * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -240,8 +308,8 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;  // chunk counter across tiles -> accumulator ring slot and parity
@@ -264,17 +332,17 @@ corr_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per k-step inside the swizzle row
-              umma_f16(tmem_d, da_hi + adv, db_hi + adv, IDESC, (kb != kb0 || ks != 0) ? 1u : 0u);
-              umma_f16(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
-              umma_f16(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
+              umma_f16_elect(tmem_d, da_hi + adv, db_hi + adv, IDESC, (kb != kb0 || ks != 0) ? 1u : 0u);
+              umma_f16_elect(tmem_d, da_hi + adv, db_lo + adv, IDESC, 1u);
+              umma_f16_elect(tmem_d, da_lo + adv, db_hi + adv, IDESC, 1u);
             }
-            umma_commit_mc(empty_bar + 8 * stage, (uint16_t)3);  // stage free (in both CTAs) once these MMAs retire
+            umma_commit_mc_elect(empty_bar + 8 * stage, (uint16_t)3);  // stage free (in both CTAs) once these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(tfull_bar + 8 * acc);  // chunk accumulator complete
+          umma_commit_elect(tfull_bar + 8 * acc);  // chunk accumulator complete
         }
       }
     }
