@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 1
+#define MCD_ABI_VERSION 2
 
 typedef struct mcd_context* mcd_handle;
 
@@ -70,6 +70,16 @@ typedef struct {
   double step_ms[MCD_MAX_STEP_STATS];
   int64_t step_rounds[MCD_MAX_STEP_STATS];
   int64_t step_bids[MCD_MAX_STEP_STATS];
+  /* Dual certificate of the assignment solves (handle option "certify", on by default): for every step the
+   * solver's final object prices are turned into a feasible point of the dual of the reference's ILP
+   * (macrodna.py:27-84) whose objective D bounds every feasible assignment from above; gap = D - objective >= 0
+   * is 0 to rounding iff the step's assignment is optimal.  A relative gap above 1e-9 (the north-star objective
+   * tolerance) fails the call with MCD_ERR_NOT_CONVERGED. */
+  double cert_rel_gap;       /* max over the steps of gap / |objective|                              */
+  double cert_max_violation; /* largest single dual-feasibility violation of a matched edge, any step */
+  int64_t cert_bad;          /* unassigned persons + doubly used objects found by the checker (0)     */
+  int64_t cert_steps;        /* steps certified                                                       */
+  double step_cert_gap[MCD_MAX_STEP_STATS]; /* per-step relative gap (-1: not certified)              */
 } mcd_stats;
 
 int mcd_abi_version(void);
@@ -84,6 +94,17 @@ int mcd_device_sm_count(mcd_handle h);
 int mcd_synchronize(mcd_handle h);
 /* The handle's cudaStream_t (as void*), for callers that record events on it. */
 void* mcd_stream(mcd_handle h);
+
+/*
+ * Behaviour / tuning switches of a handle (all have working defaults; nothing on the product path reads the
+ * environment).  Names: "certify" (1), "debug" (0: per-step solver counters on stderr), "ozaki.slices" (0 = auto),
+ * "ozaki.align", "ozaki.plan", "k1.generic", and the solver knobs "lap.theta", "lap.eps_min", "lap.scaling",
+ * "lap.max_rounds", "lap.blocks_per_sm", "lap.grid_blocks", "lap.list_max_m", "lap.lists", "lap.list_min_nu",
+ * "lap.tail_cluster", "lap.tail_mh", "lap.tail_nu", "lap.aug_nu", "lap.aug_nu_square", "lap.rank_select",
+ * "lap.min_chunk", "lap.chunk_waves".  Unknown names return MCD_ERR_INVALID.
+ */
+int mcd_set_option(mcd_handle h, const char* name, double value);
+int mcd_get_option(mcd_handle h, const char* name, double* value);
 
 /*
  * K1 -- per-cell standardisation.  Replaces the per-operand half of
@@ -107,11 +128,13 @@ int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t
 /* Same pass, but emits the integer operand of MCD_PREC_OZAKI_INT8: every unit-norm centred row, scaled by a
  * per-row power of two so that max|.| lies in [0.25, 0.5), as `nsl` balanced radix-128 digit slices:
  *   digits [nsl, ncells, ldk8] int8, ldk8 = mcd_padded_k_split(G), zero padded;  scale [ncells] = 2^-e (the
- *   factor that undoes the row scaling);  nsl in [2, 8] (mcd_ozaki_default_slices(): 6, env MCD_OZAKI_SLICES). */
+ *   factor that undoes the row scaling);  nsl in [2, 8] (mcd_ozaki_default_slices(): 6). */
 int mcd_ozaki_default_slices(void);
 /* Slice count the fused driver uses for an M x N x G instance: 8 (FP64-GEMM-level error) while M*N*G <= 2e11,
- * 6 (~1e-12 absolute) above; MCD_OZAKI_SLICES overrides. */
+ * 6 (~1e-12 absolute) above; the handle option "ozaki.slices" overrides. */
 int mcd_ozaki_slices_for(int64_t M, int64_t N, int64_t G);
+/* The slice count a given handle will use: its "ozaki.slices" option if set, else mcd_ozaki_slices_for. */
+int mcd_ozaki_slices(mcd_handle h, int64_t M, int64_t N, int64_t G);
 int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
                           int nsl, double* scale, double* norms);
 /* Synchronise and return MCD_ERR_NONFINITE if any standardise call since the last check saw NaN/Inf. */
@@ -146,6 +169,17 @@ int mcd_corr_ozaki(mcd_handle h, const int8_t* A8, int64_t M, const int8_t* B8, 
  */
 int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
                 double* objective);
+/* Same solve, also returning the proof of optimality: prices [m] float64 DEVICE out (the final object prices =
+ * dual variables v_j, may be NULL) and cert [4] float64 HOST out = {relative duality gap, absolute gap, largest
+ * single violation, #invalid entries} as described at mcd_stats (may be NULL).  The gap is recomputed from W, the
+ * prices and col4row alone, so it does not depend on how the solver got there. */
+int mcd_lap_max_certified(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                          double* objective, double* prices, double* cert);
+/* The checker alone, on ANY assignment / price vector for W (all DEVICE; cert [4] HOST as above): lets a caller
+ * certify a result obtained elsewhere, and lets the tests show that a damaged assignment or damaged prices are
+ * caught.  Always returns MCD_OK when it ran; the verdict is in cert. */
+int mcd_lap_certify(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, const int32_t* col4row,
+                    const double* prices, double* cert);
 
 /*
  * K3+K4 -- the whole step loop (macrodna.py:110-145) on a resident correlation matrix.

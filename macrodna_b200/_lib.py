@@ -45,6 +45,11 @@ class McdStats(C.Structure):
         ("step_ms", C.c_double * MAX_STEP_STATS),
         ("step_rounds", C.c_int64 * MAX_STEP_STATS),
         ("step_bids", C.c_int64 * MAX_STEP_STATS),
+        ("cert_rel_gap", C.c_double),
+        ("cert_max_violation", C.c_double),
+        ("cert_bad", C.c_int64),
+        ("cert_steps", C.c_int64),
+        ("step_cert_gap", C.c_double * MAX_STEP_STATS),
     ]
 
     def as_dict(self):
@@ -54,6 +59,9 @@ class McdStats(C.Structure):
         d["step_ms"] = [self.step_ms[i] for i in range(n)]
         d["step_rounds"] = [self.step_rounds[i] for i in range(n)]
         d["step_bids"] = [self.step_bids[i] for i in range(n)]
+        for k in ("cert_rel_gap", "cert_max_violation", "cert_bad", "cert_steps"):
+            d[k] = getattr(self, k)
+        d["step_cert_gap"] = [self.step_cert_gap[i] for i in range(n)]
         return d
 
 
@@ -68,6 +76,8 @@ SIGNATURES = {
     "mcd_device_sm_count": (_I, [_VP]),
     "mcd_synchronize": (_I, [_VP]),
     "mcd_stream": (_VP, [_VP]),
+    "mcd_set_option": (_I, [_VP, C.c_char_p, _D]),
+    "mcd_get_option": (_I, [_VP, C.c_char_p, C.POINTER(_D)]),
     "mcd_padded_k": (_I64, [_I64]),
     "mcd_padded_k_split": (_I64, [_I64]),
     "mcd_num_steps": (_I64, [_I64, _I64]),
@@ -75,6 +85,7 @@ SIGNATURES = {
     "mcd_standardize_split": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
     "mcd_ozaki_default_slices": (_I, []),
     "mcd_ozaki_slices_for": (_I, [_I64, _I64, _I64]),
+    "mcd_ozaki_slices": (_I, [_VP, _I64, _I64, _I64]),
     "mcd_standardize_ozaki": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I, _VP, _VP]),
     "mcd_corr_ozaki": (_I, [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _I64]),
     "mcd_check_finite": (_I, [_VP]),
@@ -83,6 +94,8 @@ SIGNATURES = {
     "mcd_transpose_f64": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _I64]),
     "mcd_last_match_values": (_I, [_VP, _VP, _I64, _I]),
     "mcd_lap_max": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP]),
+    "mcd_lap_max_certified": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP]),
+    "mcd_lap_certify": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP]),
     "mcd_subinstance_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
     "mcd_corr_rows": (_I, [_VP, _VP, _I64, _VP, _I]),
     "mcd_corr_pairs": (_I, [_VP, _VP, _VP, _I64, _VP]),
@@ -116,7 +129,7 @@ def load_library():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.mcd_abi_version() != 1:
+    if lib.mcd_abi_version() != 2:
         raise RuntimeError("libmacrodna_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -136,6 +149,26 @@ def _ptr(x):
     return int(x)
 
 
+def _matrix(x, rows, ld, name):
+    """A host operand of the C ABI: C-contiguous float64 [rows, ld].  Anything else (float32, a Fortran-ordered or
+    transposed view such as ``df.to_numpy().T``, a wrong shape) would be silently reinterpreted by the pointer
+    hand-off, so it is converted (dtype / layout) or rejected (shape) here.  Device pointers pass through."""
+    if not isinstance(x, np.ndarray):
+        return x
+    if x.ndim != 2 or x.shape[0] != rows or x.shape[1] != ld:
+        raise ValueError("macrodna_b200: %s must have shape (%d, %d), got %r" % (name, rows, ld, x.shape))
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _out(x, n, dtype, name):
+    """A caller-provided host output vector: must already be a writable C-contiguous array of the right type."""
+    if isinstance(x, np.ndarray):
+        if x.dtype != dtype or not x.flags.c_contiguous or not x.flags.writeable or x.size < n:
+            raise ValueError("macrodna_b200: %s must be a writable C-contiguous %s array of at least %d elements" % (
+                name, np.dtype(dtype).name, n))
+    return x
+
+
 class Handle:
     """One CUDA device + stream + workspace.  Created lazily so objects holding it stay picklable."""
 
@@ -151,11 +184,13 @@ class Handle:
             )
         self.h = h
         self.device = device
+        self.pid = os.getpid()  # a CUDA context does not survive fork(): api.get_handle checks this
         self.resident_token = None  # identifies the run whose correlation matrix is resident (api.MaCroDNA)
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.mcd_destroy(self.h)
+            if getattr(self, "pid", None) == os.getpid():  # in a forked child the context is not ours to destroy
+                self.lib.mcd_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -170,6 +205,15 @@ class Handle:
             if st == MCD_ERR_NONFINITE or st == MCD_ERR_INVALID:
                 raise ValueError("macrodna_b200: " + detail)
             raise McdError(st, detail)
+
+    def set_option(self, name, value):
+        """Tuning / behaviour switch of this handle (``mcd_set_option``; names in include/macrodna_b200.h)."""
+        self.check(self.lib.mcd_set_option(self.h, name.encode(), float(value)))
+
+    def get_option(self, name):
+        v = C.c_double()
+        self.check(self.lib.mcd_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
 
     @property
     def sm_count(self):
@@ -187,6 +231,14 @@ class Handle:
         operand's block (the gene intersection is then gathered on the device)."""
         self.resident_token = None  # whoever relied on the previous resident correlation matrix must recompute
         nsteps = self.lib.mcd_num_steps(M, N)
+        if in_space == MEM_HOST:
+            rna = _matrix(rna, M, ld_rna or G, "rna")
+            dna = _matrix(dna, N, ld_dna or G, "dna")
+        if out_space == MEM_HOST:
+            assign = _out(assign, M, np.int32, "assign")
+            step = _out(step, M, np.int32, "step")
+            step_obj = _out(step_obj, nsteps, np.float64, "step_obj")
+            corr_out = _out(corr_out, M * N, np.float64, "corr_out")
         if assign is None:
             assign = np.empty(M, dtype=np.int32)
         if step is None:

@@ -11,6 +11,8 @@ the step loop -- runs in the CUDA library behind the C ABI
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pandas as pd
 
@@ -20,8 +22,22 @@ _HANDLES = {}
 
 
 def get_handle(device: int = 0) -> "_lib.Handle":
-    """Per-process, per-device library context (created on first use, so instances pickle)."""
+    """Per-process, per-device library context (created on first use, so instances pickle).
+
+    The reference's sweep scripts run the class in the parent and then fork a ``multiprocessing.Pool``
+    (clonal_proportions_resampling.py:266-267, :300): a CUDA context does not survive ``fork()``, so a handle
+    inherited from another process is never touched.  A child that inherited one is told how to run instead
+    (CUDA cannot be re-initialised in a forked child); a child of a parent that had not used the GPU yet simply
+    creates its own context."""
     h = _HANDLES.get(device)
+    if h is not None and getattr(h, "pid", None) != os.getpid():
+        # inherited over fork(): the parent had already initialised CUDA in this address space
+        raise RuntimeError(
+            "macrodna_b200: this process was fork()ed from a process that had already used the GPU (pid %s); CUDA "
+            "cannot be re-initialised in a forked child.  Start the workers with "
+            "multiprocessing.get_context('spawn') (or 'forkserver'), or run the replicates in the parent with "
+            "MaCroDNA.subinstance_assignment / macrodna_b200.dist.sweep_assignments, which keep many replicates in "
+            "flight on the GPU." % (h.pid,))
     if h is None or h.h is None:
         h = _lib.Handle(device)
         _HANDLES[device] = h
@@ -85,6 +101,7 @@ class MaCroDNA:
         self._rna_df = df
         self._rna_filtered = False
         self._genes = None
+        self._resident_token = None  # the resident correlation matrix belongs to the old frames
 
     @property
     def dna_df(self):
@@ -98,6 +115,7 @@ class MaCroDNA:
         self._dna_df = df
         self._dna_filtered = False
         self._genes = None
+        self._resident_token = None
 
     # -- host bookkeeping -------------------------------------------------------------------------
     def _shared_genes(self):

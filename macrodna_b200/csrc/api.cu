@@ -1,6 +1,7 @@
 // C ABI of the hot path (include/macrodna_b200.h): context, workspace, step loop (K4), fused driver.
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <new>
 
@@ -140,19 +141,81 @@ int mcd_standardize_split(mcd_handle h, const double* X, int64_t ncells, int64_t
   return mcd_launch_standardize(h, X, ncells, G, ldx, nullptr, 0, slices, slices + ncells * ldk16, ldk16, norms);
 }
 
-int mcd_ozaki_default_slices(void) {
-  const char* e = getenv("MCD_OZAKI_SLICES");
-  int v = e ? atoi(e) : 6;
-  if (v < 2) v = 2;
-  if (v > MCD_OZAKI_MAX_SLICES) v = MCD_OZAKI_MAX_SLICES;
-  return v;
-}
+int mcd_ozaki_default_slices(void) { return 6; }
 
 int mcd_ozaki_slices_for(int64_t M, int64_t N, int64_t G) {
-  if (getenv("MCD_OZAKI_SLICES")) return mcd_ozaki_default_slices();
   // 8 slices (36 products, error at the level of an FP64 GEMM's own rounding) while the contraction is cheap
   // anyway; 6 slices (21 products, ~1e-12 absolute) once it is the large-instance bottleneck
   return (double)M * (double)N * (double)G <= 2.0e11 ? 8 : 6;
+}
+
+int mcd_ozaki_slices(mcd_handle h, int64_t M, int64_t N, int64_t G) {
+  if (h != nullptr && h->opt.ozaki_slices >= 2)
+    return h->opt.ozaki_slices > MCD_OZAKI_MAX_SLICES ? MCD_OZAKI_MAX_SLICES : h->opt.ozaki_slices;
+  return mcd_ozaki_slices_for(M, N, G);
+}
+
+namespace {
+struct OptEntry {
+  const char* name;
+  int is_double;
+  size_t off;
+};
+#define MCD_OPT_I(n, f) {n, 0, offsetof(mcd_options, f)}
+#define MCD_OPT_D(n, f) {n, 1, offsetof(mcd_options, f)}
+const OptEntry kOptions[] = {
+    MCD_OPT_I("certify", certify),
+    MCD_OPT_I("debug", debug),
+    MCD_OPT_I("ozaki.slices", ozaki_slices),
+    MCD_OPT_I("ozaki.align", ozaki_align),
+    MCD_OPT_I("ozaki.plan", ozaki_plan),
+    MCD_OPT_I("k1.generic", k1_generic),
+    MCD_OPT_D("lap.theta", lap_theta),
+    MCD_OPT_D("lap.eps_min", lap_eps_min),
+    MCD_OPT_I("lap.scaling", lap_scaling),
+    MCD_OPT_D("lap.max_rounds", lap_max_rounds),
+    MCD_OPT_I("lap.blocks_per_sm", lap_blocks_per_sm),
+    MCD_OPT_I("lap.grid_blocks", lap_grid_blocks),
+    MCD_OPT_I("lap.list_max_m", lap_list_max_m),
+    MCD_OPT_I("lap.lists", lap_lists),
+    MCD_OPT_I("lap.list_min_nu", lap_list_min_nu),
+    MCD_OPT_I("lap.tail_cluster", lap_tail_cluster),
+    MCD_OPT_I("lap.tail_mh", lap_tail_mh),
+    MCD_OPT_I("lap.tail_nu", lap_tail_nu),
+    MCD_OPT_I("lap.aug_nu", lap_aug_nu),
+    MCD_OPT_I("lap.aug_nu_square", lap_aug_nu_square),
+    MCD_OPT_I("lap.rank_select", lap_rank_select),
+    MCD_OPT_I("lap.min_chunk", lap_min_chunk),
+    MCD_OPT_I("lap.chunk_waves", lap_chunk_waves),
+};
+const OptEntry* find_option(const char* name) {
+  if (name == nullptr) return nullptr;
+  for (const OptEntry& e : kOptions)
+    if (strcmp(e.name, name) == 0) return &e;
+  return nullptr;
+}
+}  // namespace
+
+int mcd_set_option(mcd_handle h, const char* name, double value) {
+  if (!h) return MCD_ERR_INVALID;
+  const OptEntry* e = find_option(name);
+  if (e == nullptr || !(value == value)) return mcd_fail(h, MCD_ERR_INVALID, "mcd_set_option: unknown option or NaN value");
+  char* base = reinterpret_cast<char*>(&h->opt);
+  if (e->is_double)
+    *reinterpret_cast<double*>(base + e->off) = value;
+  else
+    *reinterpret_cast<int*>(base + e->off) = (int)value;
+  return MCD_OK;
+}
+
+int mcd_get_option(mcd_handle h, const char* name, double* value) {
+  if (!h || !value) return MCD_ERR_INVALID;
+  const OptEntry* e = find_option(name);
+  if (e == nullptr) return mcd_fail(h, MCD_ERR_INVALID, "mcd_get_option: unknown option");
+  const char* base = reinterpret_cast<const char*>(&h->opt);
+  *value = e->is_double ? *reinterpret_cast<const double*>(base + e->off)
+                        : (double)*reinterpret_cast<const int*>(base + e->off);
+  return MCD_OK;
 }
 
 int mcd_standardize_ozaki(mcd_handle h, const double* X, int64_t ncells, int64_t G, int64_t ldx, int8_t* digits,
@@ -214,20 +277,68 @@ int mcd_corr_split(mcd_handle h, const uint16_t* A3, int64_t M, const uint16_t* 
   return mcd_launch_corr_split(h, A3, A3 + M * ldk16, M, B3, B3 + N * ldk16, N, ldk16, nA, nB, C, ldc, Ct, ldct);
 }
 
-int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
-                double* objective) {
+static int lap_max_impl(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                        double* objective, double* prices, double* cert_out) {
   if (!h) return MCD_ERR_INVALID;
   if (!W || !col4row || n < 0 || m < n || ldw < m) return mcd_fail(h, MCD_ERR_INVALID, "mcd_lap_max arguments");
   MCD_CUDA(h, cudaSetDevice(h->device));
   void* work = nullptr;
-  int st = mcd_ws(h, WS_LAP, mcd_lap_workspace_bytes(n, m) + 256, &work);
+  int st = mcd_ws(h, WS_LAP, mcd_lap_workspace_bytes(n, m) + 512, &work);
   if (st) return st;
-  // counters live in the first 256 bytes of the slot
+  // counters and certificate live in the first 512 bytes of the slot
   mcd_lap_counters* cnt = static_cast<mcd_lap_counters*>(work);
-  MCD_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(mcd_lap_counters), h->stream));
-  int st2 = mcd_launch_lap(h, W, n, m, ldw, col4row, objective, static_cast<char*>(work) + 256, cnt, true);
+  mcd_lap_cert* cert = reinterpret_cast<mcd_lap_cert*>(static_cast<char*>(work) + 256);
+  MCD_CUDA(h, cudaMemsetAsync(work, 0, 512, h->stream));
+  int st2 = mcd_launch_lap(h, W, n, m, ldw, col4row, objective, static_cast<char*>(work) + 512, cnt, true, cert, prices);
   if (st2) return st2;
-  return mcd_check_finite(h);
+  mcd_lap_counters hc;
+  mcd_lap_cert hcert;
+  MCD_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof hc, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(&hcert, cert, sizeof hcert, cudaMemcpyDeviceToHost, h->stream));
+  if ((st = mcd_check_finite(h))) return st;  // synchronises
+  if (cert_out) {
+    cert_out[0] = hcert.rel_gap;
+    cert_out[1] = hcert.gap;
+    cert_out[2] = hcert.max_violation;
+    cert_out[3] = (double)hcert.n_bad;
+  }
+  if (n > 0 && (hc.status & 1)) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a person was left unassigned");
+  if (n > 0 && (hc.status & 2)) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "the dual certificate of the assignment failed");
+  return MCD_OK;
+}
+
+int mcd_lap_certify(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, const int32_t* col4row,
+                    const double* prices, double* cert_out) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!W || !col4row || !prices || !cert_out || n < 1 || m < n || ldw < m || m > 0x3fffffff)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_lap_certify arguments");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  void* work = nullptr;
+  int st = mcd_ws(h, WS_LAP, 512 + (size_t)m * 4 + (size_t)n * 8 + 1024, &work);
+  if (st) return st;
+  mcd_lap_counters* cnt = static_cast<mcd_lap_counters*>(work);
+  mcd_lap_cert* cert = reinterpret_cast<mcd_lap_cert*>(static_cast<char*>(work) + 256);
+  MCD_CUDA(h, cudaMemsetAsync(work, 0, 512, h->stream));
+  if ((st = mcd_launch_lap_certify(h, W, n, m, ldw, col4row, prices, static_cast<char*>(work) + 512, cert, cnt)))
+    return st;
+  mcd_lap_cert hcert;
+  MCD_CUDA(h, cudaMemcpyAsync(&hcert, cert, sizeof hcert, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  cert_out[0] = hcert.rel_gap;
+  cert_out[1] = hcert.gap;
+  cert_out[2] = hcert.max_violation;
+  cert_out[3] = (double)hcert.n_bad;
+  return MCD_OK;
+}
+
+int mcd_lap_max(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                double* objective) {
+  return lap_max_impl(h, W, n, m, ldw, col4row, objective, nullptr, nullptr);
+}
+
+int mcd_lap_max_certified(mcd_handle h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
+                          double* objective, double* prices, double* cert) {
+  return lap_max_impl(h, W, n, m, ldw, col4row, objective, prices, cert);
 }
 
 }  // extern "C"
@@ -249,20 +360,22 @@ __global__ void iota_flags_kernel(int* act, int* flag, int* assign, int* step, i
 
 // W[j, k] = Ct[j, act[k]]  (persons = DNA rows of Ct, objects = still-unassigned RNA cells)
 __global__ void gather_cols_kernel(const double* __restrict__ Ct, int64_t ldct, const int* __restrict__ act, int R,
-                                   double* __restrict__ W, int64_t ldw) {
-  const int64_t j = blockIdx.y;
-  const double* src = Ct + j * ldct;
-  double* dst = W + j * ldw;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) dst[k] = src[act[k]];
+                                   double* __restrict__ W, int64_t ldw, int64_t nrows) {
+  for (int64_t j = blockIdx.y; j < nrows; j += gridDim.y) {  // gridDim.y is capped at 65535
+    const double* src = Ct + j * ldct;
+    double* dst = W + j * ldw;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) dst[k] = src[act[k]];
+  }
 }
 
 // W[k, :] = C[act[k], :]  (persons = still-unassigned RNA cells, objects = DNA cells)
 __global__ void gather_rows_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ act, int N,
-                                   double* __restrict__ W, int64_t ldw) {
-  const int64_t k = blockIdx.y;
-  const double* src = C + (int64_t)act[k] * ldc;
-  double* dst = W + k * ldw;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) dst[j] = src[j];
+                                   double* __restrict__ W, int64_t ldw, int64_t nrows) {
+  for (int64_t k = blockIdx.y; k < nrows; k += gridDim.y) {
+    const double* src = C + (int64_t)act[k] * ldc;
+    double* dst = W + k * ldw;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) dst[j] = src[j];
+  }
 }
 
 // persons were DNA cells: col4row[j] = index into act
@@ -344,19 +457,21 @@ __global__ void gather_match_kernel(const double* __restrict__ C, int64_t ldc, c
 __global__ void gather_sub_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
                                   const int* __restrict__ cols, int64_t m, int64_t n, double* __restrict__ sub,
                                   int64_t lds) {
-  const int64_t i = blockIdx.y;
-  const double* src = C + (int64_t)(rows ? rows[i] : i) * ldc;
-  double* dst = sub + i * lds;
-  for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-    dst[j] = src[cols ? cols[j] : j];
+  for (int64_t i = blockIdx.y; i < m; i += gridDim.y) {
+    const double* src = C + (int64_t)(rows ? rows[i] : i) * ldc;
+    double* dst = sub + i * lds;
+    for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+      dst[j] = src[cols ? cols[j] : j];
+  }
 }
 
 __global__ void gather_rows_out_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
-                                       int64_t n, double* __restrict__ out) {
-  const int64_t i = blockIdx.y;
-  const double* src = C + (int64_t)rows[i] * ldc;
-  for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-    out[i * n + j] = src[j];
+                                       int64_t nrows, int64_t n, double* __restrict__ out) {
+  for (int64_t i = blockIdx.y; i < nrows; i += gridDim.y) {
+    const double* src = C + (int64_t)rows[i] * ldc;
+    for (int64_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+      out[i * n + j] = src[j];
+  }
 }
 
 __global__ void gather_pairs_kernel(const double* __restrict__ C, int64_t ldc, const int* __restrict__ rows,
@@ -364,6 +479,9 @@ __global__ void gather_pairs_kernel(const double* __restrict__ C, int64_t ldc, c
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) out[k] = C[(int64_t)rows[k] * ldc + cols[k]];
 }
+
+// rows of a gather go to gridDim.y, which the hardware caps at 65535: the kernels loop over the rest
+inline unsigned grid_rows(int64_t rows) { return (unsigned)(rows < 65535 ? (rows < 1 ? 1 : rows) : 65535); }
 
 cudaEvent_t get_event(mcd_context* h, size_t idx) {
   while (h->ev.size() <= idx) {
@@ -399,12 +517,93 @@ StepPlan plan_steps(int64_t M, int64_t N) {
   return p;
 }
 
+// Device-side outputs of one step loop, carved out of one block: assign[M], step[M], obj[nsteps], one counter
+// block and one dual certificate per step.
+struct StepOut {
+  int* assign;
+  int* step;
+  double* obj;
+  mcd_lap_counters* cnt;
+  mcd_lap_cert* cert;
+};
+size_t step_out_bytes(int64_t M, int64_t nsteps) {
+  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
+  return 2 * mi + ob + (sizeof(mcd_lap_counters) + sizeof(mcd_lap_cert)) * (size_t)nsteps;
+}
+StepOut carve_step_out(void* base, int64_t M, int64_t nsteps) {
+  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
+  char* mb = static_cast<char*>(base);
+  StepOut o;
+  o.assign = reinterpret_cast<int*>(mb);
+  o.step = reinterpret_cast<int*>(mb + mi);
+  o.obj = reinterpret_cast<double*>(mb + 2 * mi);
+  o.cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
+  o.cert = reinterpret_cast<mcd_lap_cert*>(mb + 2 * mi + ob + sizeof(mcd_lap_counters) * (size_t)nsteps);
+  return o;
+}
+
+// Host side of the per-step records: fills the solver part of `stats`, prints the debug lines, returns the OR of
+// the steps' status bits (1 = a cell left unassigned, 2 = dual certificate failed).
+int fold_step_records(mcd_context* h, int64_t M, int64_t N, int64_t nsteps, const mcd_lap_counters* hc,
+                      const mcd_lap_cert* hcert, mcd_stats* stats, size_t ev_lap, bool have_events) {
+  int bad = 0;
+  if (h->opt.debug) {
+    int64_t R = M;
+    for (int64_t s = 0; s < nsteps; ++s, R -= N) {
+      const int64_t mm = R > N ? R : N;
+      fprintf(stderr, "[lap step %lld] n=%lld m=%lld rounds=%lld bids=%lld sweeps=%lld aug=%lld/%lld cert_gap=%.3e cyc=",
+              (long long)s, (long long)(R > N ? N : R), (long long)mm, hc[s].rounds, hc[s].bids, hc[s].bytes / (mm * 8),
+              hc[s].aug_rows, hc[s].aug_steps, hcert[s].rel_gap);
+      for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].t_phase[q]);
+      fprintf(stderr, "\n");
+    }
+  }
+  for (int64_t s = 0; s < nsteps; ++s) {
+    bad |= hc[s].status;
+    if (!stats) continue;
+    stats->lap_rounds += hc[s].rounds;
+    stats->lap_bids += hc[s].bids;
+    stats->lap_bytes += hc[s].bytes;
+    stats->lap_aug_rows += hc[s].aug_rows;
+    stats->lap_aug_steps += hc[s].aug_steps;
+    for (int q = 0; q < 8; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
+    if (h->opt.certify) {
+      if (hcert[s].rel_gap > stats->cert_rel_gap) stats->cert_rel_gap = hcert[s].rel_gap;
+      if (hcert[s].max_violation > stats->cert_max_violation) stats->cert_max_violation = hcert[s].max_violation;
+      stats->cert_bad += hcert[s].n_bad;
+      stats->cert_steps += 1;
+    }
+    if (s < MCD_MAX_STEP_STATS) {
+      if (have_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, get_event(h, ev_lap + s), get_event(h, ev_lap + s + 1));
+        stats->step_ms[s] = ms;
+      }
+      stats->step_rounds[s] = hc[s].rounds;
+      stats->step_bids[s] = hc[s].bids;
+      stats->step_cert_gap[s] = h->opt.certify ? hcert[s].rel_gap : -1.0;
+    }
+  }
+  return bad;
+}
+
+int step_status(mcd_context* h, int bad) {
+  if (bad & 1) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  if (bad & 2) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "the dual certificate of a step's assignment failed");
+  return MCD_OK;
+}
+
 // Enqueue the whole step loop on h->stream (no host synchronisation: every step's shape is known
 // up front because each non-final step matches exactly N RNA cells).
 // Device outputs: d_assign[M], d_step[M], d_obj[nsteps], d_counters[nsteps].
 int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M,
-                      int64_t N, int* d_assign, int* d_step, double* d_obj, mcd_lap_counters* d_counters,
-                      size_t ev_base, bool check_finite) {
+                      int64_t N, const StepOut& out, size_t ev_base, bool check_finite, bool record_events = true) {
+  int* d_assign = out.assign;
+  int* d_step = out.step;
+  double* d_obj = out.obj;
+  mcd_lap_counters* d_counters = out.cnt;
   const StepPlan plan = plan_steps(M, N);
   void* wbuf = nullptr;
   void* lapbuf = nullptr;
@@ -421,14 +620,14 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
   int* col4row = reinterpret_cast<int*>(sb + 3 * mi);
   double* W = static_cast<double*>(wbuf);
 
-  MCD_CUDA(h, cudaMemsetAsync(d_counters, 0, sizeof(mcd_lap_counters) * plan.nsteps, h->stream));
+  MCD_CUDA(h, cudaMemsetAsync(d_counters, 0, (sizeof(mcd_lap_counters) + sizeof(mcd_lap_cert)) * plan.nsteps, h->stream));
   iota_flags_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(act[0], flag, d_assign, d_step, (int)M);
   MCD_LAUNCH_CHECK(h, "iota_flags_kernel");
 
   int64_t R = M;
   int cur = 0;
   for (int64_t s = 0; s < plan.nsteps; ++s) {
-    if (s < MCD_MAX_STEP_STATS) MCD_CUDA(h, cudaEventRecord(get_event(h, ev_base + s), h->stream));
+    if (record_events && s < MCD_MAX_STEP_STATS) MCD_CUDA(h, cudaEventRecord(get_event(h, ev_base + s), h->stream));
     if (R > N) {
       // all N DNA cells take one RNA cell each (macrodna.py:29,53 with n_min = N)
       const double* Wp;
@@ -438,12 +637,13 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
         ldw = ldct;
       } else {
         ldw = (R + 1) & ~1LL;
-        dim3 grid((unsigned)((R + 1023) / 1024 < 64 ? (R + 1023) / 1024 : 64), (unsigned)N);
-        gather_cols_kernel<<<grid, 256, 0, h->stream>>>(Ct, ldct, act[cur], (int)R, W, ldw);
+        dim3 grid((unsigned)((R + 1023) / 1024 < 64 ? (R + 1023) / 1024 : 64), grid_rows(N));
+        gather_cols_kernel<<<grid, 256, 0, h->stream>>>(Ct, ldct, act[cur], (int)R, W, ldw, N);
         MCD_LAUNCH_CHECK(h, "gather_cols_kernel");
         Wp = W;
       }
-      if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0)))
+      if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0,
+                               out.cert + s)))
         return st;
       record_dna_major_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(col4row, (int)N, act[cur], d_assign,
                                                                                  d_step, flag, (int)(s + 1));
@@ -462,12 +662,13 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
         ldw = ldc;
       } else {
         ldw = (N + 1) & ~1LL;
-        dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), (unsigned)R);
-        gather_rows_kernel<<<grid, 256, 0, h->stream>>>(C, ldc, act[cur], (int)N, W, ldw);
+        dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), grid_rows(R));
+        gather_rows_kernel<<<grid, 256, 0, h->stream>>>(C, ldc, act[cur], (int)N, W, ldw, R);
         MCD_LAUNCH_CHECK(h, "gather_rows_kernel");
         Wp = W;
       }
-      if ((st = mcd_launch_lap(h, Wp, R, N, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0)))
+      if ((st = mcd_launch_lap(h, Wp, R, N, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0,
+                               out.cert + s)))
         return st;
       record_rna_major_kernel<<<(unsigned)((R + 255) / 256), 256, 0, h->stream>>>(col4row, (int)R, act[cur], d_assign,
                                                                                  d_step, flag, (int)(s + 1));
@@ -475,8 +676,9 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
     }
     R -= N;
   }
-  MCD_CUDA(h, cudaEventRecord(
-      get_event(h, ev_base + (plan.nsteps < MCD_MAX_STEP_STATS ? plan.nsteps : MCD_MAX_STEP_STATS)), h->stream));
+  if (record_events)
+    MCD_CUDA(h, cudaEventRecord(
+        get_event(h, ev_base + (plan.nsteps < MCD_MAX_STEP_STATS ? plan.nsteps : MCD_MAX_STEP_STATS)), h->stream));
   return MCD_OK;
 }
 
@@ -539,52 +741,30 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
   h->last_assign = nullptr;
   const int64_t nsteps = mcd_num_steps(M, N);
   void* misc = nullptr;
-  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
-  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
-  int st = mcd_ws(h, WS_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc);
+  int st = mcd_ws(h, WS_MISC, step_out_bytes(M, nsteps), &misc);
   if (st) return st;
-  char* mb = static_cast<char*>(misc);
-  int* d_assign = reinterpret_cast<int*>(mb);
-  int* d_step = reinterpret_cast<int*>(mb + mi);
-  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
-  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
+  const StepOut out = carve_step_out(misc, M, nsteps);
   const int64_t launches0 = h->launches;
   const size_t EV_LAP = 8;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
-  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP, true))) return st;
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, out, EV_LAP, true))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
 
   const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)M * 4, kind, h->stream));
-  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)M * 4, kind, h->stream));
-  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(assign, out.assign, (size_t)M * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, out.step, (size_t)M * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, out.obj, (size_t)nsteps * 8, kind, h->stream));
   std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  std::vector<mcd_lap_cert> hcert((size_t)nsteps);
   int flag = 0;
-  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), out.cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(hcert.data(), out.cert, sizeof(mcd_lap_cert) * nsteps, cudaMemcpyDeviceToHost, h->stream));
   MCD_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   MCD_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
   if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the correlation matrix");
-  int bad = 0;
   if (stats) memset(stats, 0, sizeof *stats);
-  for (int64_t s = 0; s < nsteps; ++s) {
-    if (hc[s].status) bad = 1;
-    if (stats) {
-      stats->lap_rounds += hc[s].rounds;
-      stats->lap_bids += hc[s].bids;
-      stats->lap_bytes += hc[s].bytes;
-      stats->lap_aug_rows += hc[s].aug_rows;
-      stats->lap_aug_steps += hc[s].aug_steps;
-      for (int q = 0; q < 8; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
-      if (s < MCD_MAX_STEP_STATS) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));
-        stats->step_ms[s] = ms;
-        stats->step_rounds[s] = hc[s].rounds;
-        stats->step_bids[s] = hc[s].bids;
-      }
-    }
-  }
+  const int bad = fold_step_records(h, M, N, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
   if (stats) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
@@ -593,8 +773,7 @@ int mcd_lap_steps(mcd_handle h, const double* C, int64_t ldc, const double* Ct, 
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
   }
-  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
-  return MCD_OK;
+  return step_status(h, bad);
 }
 
 int mcd_cell2cell(mcd_handle h, const double* rna, int64_t ld_rna, const double* dna, int64_t ld_dna, int64_t M,
@@ -619,13 +798,16 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   }
   if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16 && precision != MCD_PREC_OZAKI_INT8)
     return mcd_fail(h, MCD_ERR_INVALID, "unknown precision");
-  const int nsl = mcd_ozaki_slices_for(M, N, G);
+  const int nsl = mcd_ozaki_slices(h, M, N, G);
   // exact int32 accumulation bounds the gene count of the integer path; longer rows use the FP64 pipe
   if (precision == MCD_PREC_OZAKI_INT8 && (double)nsl * 4096.0 * (double)mcd_padded_k_split(G) >= 2147483648.0)
     precision = MCD_PREC_FP64;
   MCD_CUDA(h, cudaSetDevice(h->device));
+  h->last_M = 0;  // whatever was resident is about to be overwritten (also on an early error return)
+  h->last_assign = nullptr;
   const int64_t launches0 = h->launches;
   enum { EV_T0 = 0, EV_H2D, EV_STD, EV_CORR, EV_LAPEND, EV_D2H, EV_LAP = 8 };
+  const size_t EV_DNA_K1 = 90;  // 2 events around the DNA operand's K1 launch
   int st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_T0), h->stream));
 
@@ -701,6 +883,7 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
     if (nchunk > 16) nchunk = 16;
   }
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_H2D), h->stream));  // DNA operand resident
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_DNA_K1), h->stream));
   // DNA operand: K1 once
   mcd_ozaki_out ozb, oza;
   ozb.digits = static_cast<int8_t*>(pb);
@@ -717,6 +900,7 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   else
     st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, b_hi, b_lo, ldk, nB, d_didx);
   if (st) return st;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, EV_DNA_K1 + 1), h->stream));
   int64_t rows_per = ((M + nchunk - 1) / nchunk + 127) / 128 * 128;
   if (rows_per < 128) rows_per = 128;
   const size_t EV_CHUNK = 100;  // 4 events per chunk: copy done, K1 start, K1 end, K2 end
@@ -768,73 +952,40 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   // ---- K3 + K4
   const int64_t nsteps = mcd_num_steps(M, N);
   void* misc = nullptr;
-  const size_t mi = ((size_t)M * 4 + 255) / 256 * 256;
-  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
-  if ((st = mcd_ws(h, WS_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc))) return st;
-  char* mb = static_cast<char*>(misc);
-  int* d_assign = reinterpret_cast<int*>(mb);
-  int* d_step = reinterpret_cast<int*>(mb + mi);
-  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
-  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
-  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, d_assign, d_step, d_obj, d_cnt, EV_LAP, false))) return st;
+  if ((st = mcd_ws(h, WS_MISC, step_out_bytes(M, nsteps), &misc))) return st;
+  const StepOut out = carve_step_out(misc, M, nsteps);
+  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, out, EV_LAP, false))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_LAPEND), h->stream));
 
   // ---- outputs
   const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)M * 4, kind, h->stream));
-  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)M * 4, kind, h->stream));
-  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(assign, out.assign, (size_t)M * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, out.step, (size_t)M * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, out.obj, (size_t)nsteps * 8, kind, h->stream));
   if (corr_out)
     MCD_CUDA(h, cudaMemcpy2DAsync(corr_out, (size_t)N * 8, C, (size_t)ldc * 8, (size_t)N * 8, (size_t)M, kind,
                                   h->stream));
   std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  std::vector<mcd_lap_cert> hcert((size_t)nsteps);
   int flag = 0;
-  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), out.cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(hcert.data(), out.cert, sizeof(mcd_lap_cert) * nsteps, cudaMemcpyDeviceToHost, h->stream));
   MCD_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   MCD_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream));
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_D2H), h->stream));
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
 
-  int bad = 0;
   if (stats) memset(stats, 0, sizeof *stats);
-  if (getenv("MCD_LAP_DEBUG")) {
-    int64_t R = M;
-    for (int64_t s = 0; s < nsteps; ++s, R -= N) {
-      const int64_t mm = R > N ? R : N;
-      fprintf(stderr, "[lap step %lld] n=%lld m=%lld rounds=%lld bids=%lld sweeps=%lld aug=%lld/%lld cyc=", (long long)s,
-              (long long)(R > N ? N : R), (long long)mm, hc[s].rounds, hc[s].bids, hc[s].bytes / (mm * 8), hc[s].aug_rows,
-              hc[s].aug_steps);
-      for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].t_phase[q]);
-      fprintf(stderr, "\n");
-    }
-  }
-  for (int64_t s = 0; s < nsteps; ++s) {
-    if (hc[s].status) bad = 1;
-    if (stats) {
-      stats->lap_rounds += hc[s].rounds;
-      stats->lap_bids += hc[s].bids;
-      stats->lap_bytes += hc[s].bytes;
-      stats->lap_aug_rows += hc[s].aug_rows;
-      stats->lap_aug_steps += hc[s].aug_steps;
-      for (int q = 0; q < 8; ++q) stats->lap_cycles[q] += hc[s].t_phase[q];
-      if (s < MCD_MAX_STEP_STATS) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, get_event(h, EV_LAP + s), get_event(h, EV_LAP + s + 1));
-        stats->step_ms[s] = ms;
-        stats->step_rounds[s] = hc[s].rounds;
-        stats->step_bids[s] = hc[s].bids;
-      }
-    }
-  }
+  const int bad = fold_step_records(h, M, N, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
   if (stats) {
     auto el = [&](int a, int b) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, get_event(h, a), get_event(h, b));
       return (double)ms;
     };
-    // K1 / K2 run per RNA chunk (interleaved with the H2D copies of the next chunk): sum the chunk spans.
-    // ms_h2d is the EXPOSED copy time: everything of [T0, last K2] that is neither K1 nor K2.
-    double k1 = 0.0, k2 = 0.0;
+    // K1 / K2 run per RNA chunk (interleaved with the H2D copies of the next chunk): sum the chunk spans, plus the
+    // DNA operand's K1 launch.  ms_h2d is the EXPOSED copy time: everything of [T0, last K2] that is neither K1 nor K2.
+    double k1 = el((int)EV_DNA_K1, (int)EV_DNA_K1 + 1), k2 = 0.0;
     for (int c = 0; c < nchunk_used; ++c) {
       k1 += el((int)EV_CHUNK + 4 * c + 1, (int)EV_CHUNK + 4 * c + 2);
       k2 += el((int)EV_CHUNK + 4 * c + 2, (int)EV_CHUNK + 4 * c + 3);
@@ -849,14 +1000,12 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
   }
-  h->last_M = 0;
-  h->last_assign = nullptr;
   if (flag) return mcd_fail(h, MCD_ERR_NONFINITE, "NaN or Inf in the expression / copy-number matrix");
-  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
+  if ((st = step_status(h, bad))) return st;
   h->last_M = M;
   h->last_N = N;
   h->last_ldc = ldc;
-  h->last_assign = d_assign;
+  h->last_assign = out.assign;
   return MCD_OK;
 }
 
@@ -878,9 +1027,9 @@ int mcd_corr_rows(mcd_handle h, const int32_t* rows, int64_t nrows, double* out,
     if ((st = mcd_ws(h, WS_SUB_C, (size_t)nrows * N * 8, &po))) return st;
     dst = static_cast<double*>(po);
   }
-  dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), (unsigned)nrows);
+  dim3 grid((unsigned)((N + 1023) / 1024 < 64 ? (N + 1023) / 1024 : 64), grid_rows(nrows));
   gather_rows_out_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const double*>(h->ws[WS_C].ptr), h->last_ldc,
-                                                      static_cast<const int*>(pi), N, dst);
+                                                      static_cast<const int*>(pi), nrows, N, dst);
   MCD_LAUNCH_CHECK(h, "gather_rows_out_kernel");
   if (out_space != MCD_MEM_DEVICE)
     MCD_CUDA(h, cudaMemcpyAsync(out, dst, (size_t)nrows * N * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -944,43 +1093,28 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
   double* subC = static_cast<double*>(pc);
   double* subCt = static_cast<double*>(pct);
   {
-    dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), (unsigned)m_sub);
+    dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), grid_rows(m_sub));
     gather_sub_kernel<<<grid, 256, 0, h->stream>>>(static_cast<const double*>(h->ws[WS_C].ptr), h->last_ldc, d_rows,
                                                    d_cols, m_sub, n_sub, subC, lds);
     MCD_LAUNCH_CHECK(h, "gather_sub_kernel");
   }
   if ((st = mcd_transpose_f64(h, subC, m_sub, n_sub, lds, subCt, ldst))) return st;
   const int64_t nsteps = mcd_num_steps(m_sub, n_sub);
-  const size_t mi = ((size_t)m_sub * 4 + 255) / 256 * 256;
-  const size_t ob = ((size_t)nsteps * 8 + 255) / 256 * 256;
-  if ((st = mcd_ws(h, WS_SUB_MISC, 2 * mi + ob + sizeof(mcd_lap_counters) * nsteps, &misc))) return st;
-  char* mb = static_cast<char*>(misc);
-  int* d_assign = reinterpret_cast<int*>(mb);
-  int* d_step = reinterpret_cast<int*>(mb + mi);
-  double* d_obj = reinterpret_cast<double*>(mb + 2 * mi);
-  mcd_lap_counters* d_cnt = reinterpret_cast<mcd_lap_counters*>(mb + 2 * mi + ob);
-  if ((st = enqueue_step_loop(h, subC, lds, subCt, ldst, m_sub, n_sub, d_assign, d_step, d_obj, d_cnt, EV_LAP, false)))
-    return st;
+  if ((st = mcd_ws(h, WS_SUB_MISC, step_out_bytes(m_sub, nsteps), &misc))) return st;
+  const StepOut out = carve_step_out(misc, m_sub, nsteps);
+  if ((st = enqueue_step_loop(h, subC, lds, subCt, ldst, m_sub, n_sub, out, EV_LAP, false))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
   const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  MCD_CUDA(h, cudaMemcpyAsync(assign, d_assign, (size_t)m_sub * 4, kind, h->stream));
-  MCD_CUDA(h, cudaMemcpyAsync(step, d_step, (size_t)m_sub * 4, kind, h->stream));
-  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, d_obj, (size_t)nsteps * 8, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(assign, out.assign, (size_t)m_sub * 4, kind, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(step, out.step, (size_t)m_sub * 4, kind, h->stream));
+  if (step_obj) MCD_CUDA(h, cudaMemcpyAsync(step_obj, out.obj, (size_t)nsteps * 8, kind, h->stream));
   std::vector<mcd_lap_counters> hc((size_t)nsteps);
-  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), d_cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<mcd_lap_cert> hcert((size_t)nsteps);
+  MCD_CUDA(h, cudaMemcpyAsync(hc.data(), out.cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h->stream));
+  MCD_CUDA(h, cudaMemcpyAsync(hcert.data(), out.cert, sizeof(mcd_lap_cert) * nsteps, cudaMemcpyDeviceToHost, h->stream));
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
-  int bad = 0;
   if (stats) memset(stats, 0, sizeof *stats);
-  for (int64_t s = 0; s < nsteps; ++s) {
-    if (hc[s].status) bad = 1;
-    if (stats) {
-      stats->lap_rounds += hc[s].rounds;
-      stats->lap_bids += hc[s].bids;
-      stats->lap_bytes += hc[s].bytes;
-      stats->lap_aug_rows += hc[s].aug_rows;
-      stats->lap_aug_steps += hc[s].aug_steps;
-    }
-  }
+  const int bad = fold_step_records(h, m_sub, n_sub, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
   if (stats) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
@@ -989,8 +1123,7 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
   }
-  if (bad) return mcd_fail(h, MCD_ERR_NOT_CONVERGED, "a step left an RNA/DNA cell unassigned");
-  return MCD_OK;
+  return step_status(h, bad);
 }
 
 int mcd_null_assignments(mcd_handle h, int64_t trials, uint64_t seed, double* sums, double* medians, int out_space) {

@@ -694,12 +694,8 @@ int mcd_launch_corr_ozaki(mcd_context* h, const int8_t* A, int64_t a_stride, int
   p.Ct = Ct;
   p.ldct = ldct;
   p.wave_counter = reinterpret_cast<unsigned int*>(h->d_flags + 8);
-  {
-    const char* e = getenv("MCD_OZAKI_ALIGN");
-    p.align_mode = e ? atoi(e) : 1;
-    e = getenv("MCD_OZAKI_PLAN");
-    p.plan_mode = e ? atoi(e) : 1;
-  }
+  p.align_mode = h->opt.ozaki_align;
+  p.plan_mode = h->opt.ozaki_plan;
   MCD_CUDA(h, cudaMemsetAsync(p.wave_counter, 0, sizeof(unsigned int), h->stream));
   MCD_CUDA(h, cudaFuncSetAttribute(corr_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;

@@ -30,7 +30,6 @@
 //            the auction's dual-feasible prices/profits and tight partial matching.
 //
 // Bound: HBM bandwidth for the row sweeps (8 B per object), L2/launch latency for the narrow rounds.
-#include <cstdlib>
 #include <type_traits>
 
 #include "mcd_internal.cuh"
@@ -2017,8 +2016,24 @@ __global__ void __launch_bounds__(JV_THREADS) lap_augment_kernel(LapState s) {
   const int tid = threadIdx.x;
   const int cur_list = ctrl->cur;
   const int nfree = ctrl->cnt[cur_list];
-  const int* freelist = s.un[cur_list];
+  int* freelist = s.un[cur_list];
   long long steps = 0, bytes = 0;
+
+  // The wide kernel appends to the bidder list with atomics, so its ORDER depends on scheduling; the augmentations
+  // below run in list order and on exact-tie instances the order decides which optimum comes out.  Sort it ascending
+  // (rank sort: the list is short): same input -> same assignment, on every run and every rank.
+  {
+    int* sorted = s.un[cur_list ^ 1];
+    for (int a = tid; a < nfree; a += JV_THREADS) {
+      const int v = freelist[a];
+      int rank = 0;
+      for (int b = 0; b < nfree; ++b) rank += (freelist[b] < v) ? 1 : 0;  // persons are distinct
+      sorted[rank] = v;
+    }
+    __syncthreads();
+    for (int a = tid; a < nfree; a += JV_THREADS) freelist[a] = sorted[a];
+    __syncthreads();
+  }
 
   for (int f = 0; f < nfree; ++f) {
     const int cur_row = freelist[f];
@@ -2212,6 +2227,133 @@ __global__ void __launch_bounds__(1024) lap_objective_kernel(const double* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Dual certificate of one solve -- independent of HOW the assignment was found.
+// Inputs: the cost block W, the assignment col4row and the object prices the solver ended with.  With
+//   lambda = min price over the assigned objects,  q_j = max(price_j - lambda, 0) >= 0,  u_i = max_j (W_ij - q_j),
+// (u, q) is feasible for the dual of the reference's ILP (macrodna.py:27-84: row sums <= 1, column sums <= 1,
+// all n rows matched), so  D = sum_i u_i + sum_j q_j  bounds EVERY feasible objective from above, whatever the
+// prices are.  The assignment's own objective is  P = sum_i W[i, c(i)], and
+//   D - P = sum_i [u_i - (W[i, c(i)] - q_c(i))]  +  sum_{j unassigned} q_j  =: gap >= 0.
+// gap == 0 (to rounding) proves optimality; gap / |P| is the certified relative distance from the optimum.
+// Also checked: every person assigned, no object used twice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lap_cert_prepare_kernel(LapState s, mcd_lap_cert* cert) {
+  __shared__ double red[32];
+  __shared__ int bad_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) bad_s = 0;
+  for (int j = tid; j < s.m; j += 1024) s.pred[j] = 0;  // pred doubles as the "object used" marks
+  __syncthreads();
+  double lam = 1.0e300;
+  int bad = 0;
+  for (int i = tid; i < s.n; i += 1024) {
+    const int c = s.col4row[i];
+    if (c < 0 || c >= s.m) {
+      bad++;
+    } else {
+      if (atomicExch(&s.pred[c], 1) != 0) bad++;
+      lam = fmin(lam, s.price[c]);
+    }
+  }
+  if (bad) atomicAdd(&bad_s, bad);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lam = fmin(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lam;
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < 32; ++q) lam = fmin(lam, red[q]);
+    cert->lambda = lam;
+    cert->n_bad = bad_s;
+    cert->max_violation = 0.0;
+    cert->gap = 0.0;
+    cert->rel_gap = 0.0;
+  }
+}
+
+// one CTA per person (grid-stride): u_i over the whole row, violation against the matched edge -> s.gam[i]
+__global__ void __launch_bounds__(256) lap_cert_rows_kernel(LapState s, const mcd_lap_cert* cert) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  const double lam = cert->lambda;
+  for (int i = blockIdx.x; i < s.n; i += gridDim.x) {
+    const double* w = s.W + (int64_t)i * s.ldw;
+    double best = -1.0e300;
+    if (s.vec) {
+      int j = 2 * tid;
+      for (; j + 3 * 512 + 1 < s.m; j += 4 * 512) {
+        double2 wv[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const double2*>(w + j + u * 512));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pv[u] = *reinterpret_cast<const double2*>(s.price + j + u * 512);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          best = fmax(best, wv[u].x - fmax(pv[u].x - lam, 0.0));
+          best = fmax(best, wv[u].y - fmax(pv[u].y - lam, 0.0));
+        }
+      }
+      for (; j < s.m; j += 512) {
+        best = fmax(best, __ldg(w + j) - fmax(s.price[j] - lam, 0.0));
+        if (j + 1 < s.m) best = fmax(best, __ldg(w + j + 1) - fmax(s.price[j + 1] - lam, 0.0));
+      }
+    } else {
+      for (int j = tid; j < s.m; j += 256) best = fmax(best, __ldg(w + j) - fmax(s.price[j] - lam, 0.0));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 1; q < 8; ++q) best = fmax(best, red[q]);
+      const int c = s.col4row[i];
+      double viol = 0.0;
+      if (c >= 0 && c < s.m) viol = best - (w[c] - fmax(s.price[c] - lam, 0.0));  // >= 0: c is one of the j
+      s.gam[i] = viol;
+    }
+    __syncthreads();
+  }
+}
+
+// fixed-order sums (deterministic bits): gap = sum of the row violations + the surplus price of unassigned objects
+__global__ void __launch_bounds__(1024) lap_cert_finish_kernel(LapState s, mcd_lap_cert* cert, const double* objective,
+                                                               double tol_rel, mcd_lap_counters* counters) {
+  __shared__ double rs[32], rm[32];
+  const int tid = threadIdx.x;
+  const double lam = cert->lambda;
+  double sum = 0.0, mx = 0.0;
+  for (int i = tid; i < s.n; i += 1024) {
+    const double v = s.gam[i];
+    sum += v;
+    mx = fmax(mx, v);
+  }
+  double surplus = 0.0;
+  for (int j = tid; j < s.m; j += 1024)
+    if (s.pred[j] == 0) surplus += fmax(s.price[j] - lam, 0.0);
+  mx = fmax(mx, surplus);
+  sum += surplus;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((tid & 31) == 0) rs[tid >> 5] = sum, rm[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < 32; ++q) sum += rs[q], mx = fmax(mx, rm[q]);
+    const double P = objective != nullptr ? *objective : 0.0;
+    // scale of the problem for the relative gap: |P|, or the summed |matched values| when P cancels
+    const double scale = fmax(fabs(P), 1.0e-300);
+    cert->gap = sum;
+    cert->max_violation = mx;
+    cert->rel_gap = sum / scale;
+    cert->primal = P;
+    if (cert->n_bad != 0 || !(sum <= tol_rel * scale + 1.0e-290)) counters->status |= 2;
+  }
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -2239,7 +2381,8 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
 }
 
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
-                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite) {
+                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite,
+                   mcd_lap_cert* d_cert, double* prices_out) {
   if (n <= 0) return MCD_OK;
   if (n > m) return mcd_fail(h, MCD_ERR_INVALID, "lap: rows must be the smaller side");
   if (m > 0x3fffffff) return mcd_fail(h, MCD_ERR_UNSUPPORTED, "lap: too many objects");
@@ -2277,17 +2420,12 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.pj1 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
   s.pj2 = reinterpret_cast<int*>(take(MAX_GRID_SLOTS * 4));
   s.pbound = reinterpret_cast<double*>(take(MAX_GRID_SLOTS * 8));
+  const mcd_options& opt = h->opt;
   {
-    const char* e2 = getenv("MCD_LAP_MIN_CHUNK");
-    int min_chunk = e2 ? atoi(e2) : 4096;
-    if (min_chunk < 2) min_chunk = 2;
+    int min_chunk = opt.lap_min_chunk < 2 ? 2 : opt.lap_min_chunk;
     int64_t mc2 = m / min_chunk;
     s.max_chunks = (int)(mc2 < 1 ? 1 : (mc2 > 256 ? 256 : mc2));
-  }
-  {
-    const char* e3 = getenv("MCD_LAP_CHUNK_WAVES");
-    s.chunk_waves = e3 ? atoi(e3) : 1;  // swept at 10k x 50k: 1 -> 554 ms, 2 -> 570, 4 -> 577 (whole solver)
-    if (s.chunk_waves < 1) s.chunk_waves = 1;
+    s.chunk_waves = opt.lap_chunk_waves < 1 ? 1 : opt.lap_chunk_waves;  // swept at 10k x 50k: 1 -> 554 ms, 2 -> 570, 4 -> 577
   }
   s.sp = reinterpret_cast<double*>(take(m * 8));
   s.pred = reinterpret_cast<int*>(take(m * 4));
@@ -2296,14 +2434,11 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.col4row = col4row;
   s.counters = d_counters;
   s.flags = h->d_flags;
-  const char* e;
-  double theta = (e = getenv("MCD_LAP_THETA")) ? atof(e) : 3.0;  // swept on 10k x 10k: 2 -> 55k rounds, 3 -> 34k, 4 -> 38k, 8 -> 51k
+  double theta = opt.lap_theta;  // swept on 10k x 10k: 2 -> 55k rounds, 3 -> 34k, 4 -> 38k, 8 -> 51k
   if (!(theta > 1.0)) theta = 3.0;
-  const double eps_min_rel = (e = getenv("MCD_LAP_EPS_MIN")) ? atof(e) : 1e-7;
-  bool square_scaling = (n == m && n > 1);
-  if ((e = getenv("MCD_LAP_NO_SCALING")) && atoi(e)) square_scaling = false;
-  s.max_rounds = 200000 + 64 * (long long)n;
-  if ((e = getenv("MCD_LAP_MAX_ROUNDS"))) s.max_rounds = atoll(e);
+  const double eps_min_rel = opt.lap_eps_min > 0.0 ? opt.lap_eps_min : 1e-7;
+  const bool square_scaling = (n == m && n > 1) && opt.lap_scaling != 0;
+  s.max_rounds = opt.lap_max_rounds >= 1.0 ? (long long)opt.lap_max_rounds : 200000 + 64 * (long long)n;
 
   // eps phases: range/theta, range/theta^2, ... >= eps_min_rel * range, then the exact eps = 0 phase
   double factors[MAX_PHASES];
@@ -2312,6 +2447,9 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     for (double f = 1.0 / theta; f >= eps_min_rel && nphases < MAX_PHASES - 1; f /= theta) factors[nphases++] = f;
   factors[nphases++] = 0.0;
 
+  // a solve that no-ops (non-finite input flag) must still leave a well-defined "nobody assigned" result behind:
+  // the record / objective / certificate kernels index with col4row
+  MCD_CUDA(h, cudaMemsetAsync(col4row, 0xFF, (size_t)n * 4, h->stream));
   lap_ctrl_init_kernel<<<1, 1, 0, h->stream>>>(s.ctrl, d_counters, 0);
   MCD_LAUNCH_CHECK(h, "lap_ctrl_init_kernel");
   if (square_scaling || check_finite) {
@@ -2321,9 +2459,9 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   int per_sm = 0;
   MCD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lap_auction_kernel, LAP_THREADS, 0));
   if (per_sm < 1) return mcd_fail(h, MCD_ERR_CUDA, "lap_auction_kernel cannot be resident");
-  int want = (e = getenv("MCD_LAP_BLOCKS_PER_SM")) ? atoi(e) : 4;
-  if (want < 1) want = 1;
+  int want = opt.lap_blocks_per_sm < 1 ? 1 : opt.lap_blocks_per_sm;
   int blocks = h->sm_count * (per_sm < want ? per_sm : want);
+  if (opt.lap_grid_blocks > 0 && opt.lap_grid_blocks < blocks) blocks = opt.lap_grid_blocks;  // concurrent solves share the chip
   if (blocks > MAX_GRID_SLOTS) blocks = MAX_GRID_SLOTS;
   // Mode selection.
   //   n < m, short rows (m <= 16384)  : candidate lists everywhere + single-CTA narrow kernel (one SM sweeps a
@@ -2334,15 +2472,14 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   //                                     almost every bid): split row sweeps + cluster kernel
   // single-CTA list tail only on request: the master/helper kernel is as fast or faster at every size measured
   // (C3 43.4 vs 44.3 ms, C4 82.8 vs 88.7 ms)
-  int list_max_m = (e = getenv("MCD_LAP_LIST_MAX_M")) ? atoi(e) : 0;
+  const int list_max_m = opt.lap_list_max_m;
   int use_lists = (n < m) ? 1 : 0;
-  if ((e = getenv("MCD_LAP_LISTS"))) use_lists = atoi(e) ? 1 : 0;
+  if (opt.lap_lists >= 0) use_lists = opt.lap_lists ? 1 : 0;
   const bool list_tail = use_lists != 0 && m <= list_max_m;
   // long rows: lists only pay in the rounds with at least a grid-full of bidders (failed lists are then swept by
   // whole CTAs in parallel); below that every row is split over the grid instead
-  int list_min_nu = 0;
-  if ((e = getenv("MCD_LAP_LIST_MIN_NU"))) list_min_nu = atoi(e);
-  int cs = (e = getenv("MCD_LAP_TAIL_CLUSTER")) ? atoi(e) : (m >= 32768 ? CL_MAX_CS : 8);
+  int list_min_nu = opt.lap_list_min_nu;
+  int cs = opt.lap_tail_cluster > 0 ? opt.lap_tail_cluster : (m >= 32768 ? CL_MAX_CS : 8);
   if (cs > CL_MAX_CS) cs = CL_MAX_CS;
   size_t tail_smem = 0;
   int mc = 0;
@@ -2362,7 +2499,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   // n < m: master/helper tail (candidate lists certify ~90 % of the bids).  n == m: eps-scaling flattens every
   // person's values, ~90 % of the lists fail (measured), so the scan-every-row cluster kernel stays.
   bool mh_tail = cluster_tail && n < m;
-  if ((e = getenv("MCD_LAP_TAIL_MH"))) mh_tail = cluster_tail && atoi(e) != 0;
+  if (opt.lap_tail_mh >= 0) mh_tail = cluster_tail && opt.lap_tail_mh != 0;
   if (mh_tail && cs != 8 && cs != 16) cs = 16;
   if (mh_tail) {
     mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
@@ -2370,16 +2507,13 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
       MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_mh_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   int tail_nu = list_tail ? TAIL_NU : (cluster_tail ? CL_NU : 0);
-  if ((e = getenv("MCD_LAP_TAIL_NU"))) {
-    const int v = atoi(e);
-    if (v >= 0 && v < tail_nu) tail_nu = v;
-  }
+  if (opt.lap_tail_nu >= 0 && opt.lap_tail_nu < tail_nu) tail_nu = opt.lap_tail_nu;
 
-  int aug_nu = (e = getenv("MCD_LAP_AUG_NU")) ? atoi(e) : 0;
-  if (n == m && (e = getenv("MCD_LAP_AUG_NU_SQUARE"))) aug_nu = atoi(e);
+  int aug_nu = opt.lap_aug_nu;
+  if (n == m && opt.lap_aug_nu_square >= 0) aug_nu = opt.lap_aug_nu_square;
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
-    int rank_select = getenv("MCD_LAP_RANK_SELECT") ? atoi(getenv("MCD_LAP_RANK_SELECT")) : 1;
+    int rank_select = opt.lap_rank_select;
     void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
                                             h->stream));
@@ -2409,7 +2543,52 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   }
   lap_augment_kernel<<<1, JV_THREADS, 0, h->stream>>>(s);
   MCD_LAUNCH_CHECK(h, "lap_augment_kernel");
-  lap_objective_kernel<<<1, 1024, 0, h->stream>>>(W, s.n, ldw, col4row, objective, d_counters);
+  double* obj_dev = objective != nullptr ? objective : reinterpret_cast<double*>(s.sc_val);  // scratch when unwanted
+  lap_objective_kernel<<<1, 1024, 0, h->stream>>>(W, s.n, ldw, col4row, obj_dev, d_counters);
   MCD_LAUNCH_CHECK(h, "lap_objective_kernel");
+  if (d_cert != nullptr && h->opt.certify) {
+    lap_cert_prepare_kernel<<<1, 1024, 0, h->stream>>>(s, d_cert);
+    MCD_LAUNCH_CHECK(h, "lap_cert_prepare_kernel");
+    int cert_blocks = h->sm_count * 8;
+    if ((int64_t)cert_blocks > n) cert_blocks = (int)n;
+    lap_cert_rows_kernel<<<cert_blocks, 256, 0, h->stream>>>(s, d_cert);
+    MCD_LAUNCH_CHECK(h, "lap_cert_rows_kernel");
+    lap_cert_finish_kernel<<<1, 1024, 0, h->stream>>>(s, d_cert, obj_dev, MCD_CERT_TOL_REL, d_counters);
+    MCD_LAUNCH_CHECK(h, "lap_cert_finish_kernel");
+  }
+  if (prices_out != nullptr)
+    MCD_CUDA(h, cudaMemcpyAsync(prices_out, s.price, (size_t)m * 8, cudaMemcpyDeviceToDevice, h->stream));
+  return MCD_OK;
+}
+
+// Stand-alone certificate of ANY (assignment, prices) pair for the problem W -- the checker is usable on results
+// that did not come from this solver (tests feed it SciPy's assignment with and without deliberate damage).
+int mcd_launch_lap_certify(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, const int32_t* col4row,
+                           const double* prices, void* work, mcd_lap_cert* d_cert, mcd_lap_counters* d_counters) {
+  if (n <= 0) return MCD_OK;
+  LapState s = {};
+  s.W = W;
+  s.n = (int)n;
+  s.m = (int)m;
+  s.ldw = ldw;
+  s.vec = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldw & 1) == 0) && ((reinterpret_cast<uintptr_t>(prices) & 15) == 0);
+  s.price = const_cast<double*>(prices);
+  s.col4row = const_cast<int*>(col4row);
+  char* p = static_cast<char*>(work);
+  s.pred = reinterpret_cast<int*>(p);
+  p += align_up(m * 4, 256);
+  s.gam = reinterpret_cast<double*>(p);
+  p += align_up(n * 8, 256);
+  double* obj = reinterpret_cast<double*>(p);
+  lap_objective_kernel<<<1, 1024, 0, h->stream>>>(W, s.n, ldw, col4row, obj, d_counters);
+  MCD_LAUNCH_CHECK(h, "lap_objective_kernel");
+  lap_cert_prepare_kernel<<<1, 1024, 0, h->stream>>>(s, d_cert);
+  MCD_LAUNCH_CHECK(h, "lap_cert_prepare_kernel");
+  int cert_blocks = h->sm_count * 8;
+  if ((int64_t)cert_blocks > n) cert_blocks = (int)n;
+  lap_cert_rows_kernel<<<cert_blocks, 256, 0, h->stream>>>(s, d_cert);
+  MCD_LAUNCH_CHECK(h, "lap_cert_rows_kernel");
+  lap_cert_finish_kernel<<<1, 1024, 0, h->stream>>>(s, d_cert, obj, MCD_CERT_TOL_REL, d_counters);
+  MCD_LAUNCH_CHECK(h, "lap_cert_finish_kernel");
   return MCD_OK;
 }

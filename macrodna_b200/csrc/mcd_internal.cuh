@@ -13,8 +13,37 @@ struct mcd_buffer {
   size_t bytes = 0;
 };
 
+// Tuning / behaviour switches of a handle (mcd_set_option / mcd_get_option, include/macrodna_b200.h).  Every knob
+// that used to be an environment variable read per solve lives here: tests and sweeps set them on the handle.
+struct mcd_options {
+  int certify = 1;            // "certify": dual certificate sweep after every assignment solve
+  int debug = 0;              // "debug": per-step solver counters on stderr
+  int ozaki_slices = 0;       // "ozaki.slices": 0 = automatic (mcd_ozaki_slices_for)
+  int ozaki_align = 1;        // "ozaki.align": wave alignment of the K2c producers
+  int ozaki_plan = 1;         // "ozaki.plan": unit order of a K2c pass
+  int k1_generic = 0;         // "k1.generic": force the generic digit kernel
+  double lap_theta = 3.0;     // "lap.theta": eps-scaling factor of the square phases
+  double lap_eps_min = 1e-7;  // "lap.eps_min": smallest relative eps of the scaling phases
+  int lap_scaling = 1;        // "lap.scaling": eps-scaling phases for n == m
+  double lap_max_rounds = 0;  // "lap.max_rounds": 0 = 200000 + 64 n
+  int lap_blocks_per_sm = 4;  // "lap.blocks_per_sm": cooperative grid of the wide rounds
+  int lap_grid_blocks = 0;    // "lap.grid_blocks": cap on that grid (0 = none); concurrent solves use a slice of the chip
+  int lap_list_max_m = 0;     // "lap.list_max_m": single-CTA list tail up to this many objects
+  int lap_lists = -1;         // "lap.lists": -1 = automatic (n < m)
+  int lap_list_min_nu = 0;    // "lap.list_min_nu"
+  int lap_tail_cluster = 0;   // "lap.tail_cluster": 0 = automatic (8, or 16 from 32768 objects)
+  int lap_tail_mh = -1;       // "lap.tail_mh": -1 = automatic (n < m)
+  int lap_tail_nu = -1;       // "lap.tail_nu": -1 = kernel default
+  int lap_aug_nu = 0;         // "lap.aug_nu"
+  int lap_aug_nu_square = -1; // "lap.aug_nu_square": -1 = lap.aug_nu
+  int lap_rank_select = 1;    // "lap.rank_select"
+  int lap_min_chunk = 4096;   // "lap.min_chunk"
+  int lap_chunk_waves = 1;    // "lap.chunk_waves"
+};
+
 struct mcd_context {
   int device = 0;
+  mcd_options opt;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -115,8 +144,25 @@ struct mcd_lap_counters {  // device-resident, one per solve
   long long t_phase[8];  // SM cycles seen by CTA 0. wide kernel: bidding, barrier 1, resolution, barrier 2;
                          // cluster kernel: scan, wait partials, resolve+send, wait packet
 };
+struct mcd_lap_cert {  // device-resident, one per solve: the dual certificate (lap.cu, lap_cert_* kernels)
+  double lambda;         // min price over the assigned objects
+  double gap;            // dual objective - primal objective >= 0 (0 to rounding <=> optimal)
+  double rel_gap;        // gap / |primal|
+  double max_violation;  // largest single term of the gap
+  double primal;
+  int n_bad;             // persons without an object + objects used twice
+  int pad;
+};
 size_t mcd_lap_workspace_bytes(int64_t n, int64_t m);
 // Solve one rectangular max-assignment (n <= m).  `work` is mcd_lap_workspace_bytes(n, m) of device memory.
 // check_finite: also scan W for NaN/Inf (raises the context's non-finite flag; the solver kernels then no-op)
+// d_cert: optional; when non-NULL (and the handle's "certify" option is on) the dual certificate of the solve is
+// written there and a failed certificate raises d_counters->status bit 1.  prices_out: optional [m] device copy of
+// the final object prices.
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
-                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite);
+                   double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite,
+                   mcd_lap_cert* d_cert = nullptr, double* prices_out = nullptr);
+// certificate of an arbitrary (col4row, prices) pair; work: >= 4 m + 8 n + 1024 bytes of device scratch
+int mcd_launch_lap_certify(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, const int32_t* col4row,
+                           const double* prices, void* work, mcd_lap_cert* d_cert, mcd_lap_counters* d_counters);
+#define MCD_CERT_TOL_REL 1.0e-9  // north-star objective tolerance; observed gaps are ~1e-15

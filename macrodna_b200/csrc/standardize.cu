@@ -495,7 +495,7 @@ int mcd_launch_standardize(mcd_context* h, const double* X, int64_t ncells, int6
   const int g = (int)G;
   if (oz.digits != nullptr && centred == nullptr && slices == nullptr && (oz.nsl == 6 || oz.nsl == 8) &&
       oz.ldk8 <= 24576 && (oz.ldk8 & 3) == 0 && (oz.slice_stride & 3) == 0 &&
-      (reinterpret_cast<uintptr_t>(oz.digits) & 3) == 0 && !(getenv("MCD_K1_GENERIC") && atoi(getenv("MCD_K1_GENERIC")))) {
+      (reinterpret_cast<uintptr_t>(oz.digits) & 3) == 0 && !h->opt.k1_generic) {
     const int64_t cap = oz.ldk8;  // the sweeps also write the zero padding up to ldk8
     if (cap <= 256) return launch_digits<32, 2>(h, X, gidx, ncells, g, ldx, norms, oz);
     if (cap <= 1024) return launch_digits<128, 2>(h, X, gidx, ncells, g, ldx, norms, oz);

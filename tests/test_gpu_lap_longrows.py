@@ -1,9 +1,7 @@
 """GPU tests of the solver's long-row machinery: lists in every wide round with the cooperative chunked rebuild,
 and the master/helper narrow-round kernel (8- and 16-CTA clusters).  Rows this long only occur at the large
 config, so three cases are genuinely long (m > 16384 / m >= 32768); the rest run the same (default) path on small
-problems, and once more with the optional single-CTA list tail (MCD_LAP_LIST_MAX_M=16384, read per solve)."""
-import os
-
+problems, and once more with the optional single-CTA list tail (handle option "lap.list_max_m" = 16384)."""
 import numpy as np
 import pytest
 
@@ -23,10 +21,10 @@ def _lap(handle, w):
 
 
 @pytest.fixture(params=["0", "16384"], ids=["master_helper_tail", "single_cta_list_tail"])
-def long_row_path(request):
-    os.environ["MCD_LAP_LIST_MAX_M"] = request.param
+def long_row_path(request, handle):
+    handle.set_option("lap.list_max_m", int(request.param))
     yield
-    del os.environ["MCD_LAP_LIST_MAX_M"]
+    handle.set_option("lap.list_max_m", 0)
 
 
 def _clustered(rng, n, m, k):
