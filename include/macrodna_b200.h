@@ -246,6 +246,21 @@ int mcd_last_match_values(mcd_handle h, double* out, int64_t M, int out_space);
  */
 int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols, int64_t n_sub,
                           int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats);
+/*
+ * mcd_subinstance_sweep: `nrep` replicates of mcd_subinstance_steps in one call -- the reference's resampling
+ * sweeps (clonal_proportions_resampling.py:172-201 under multiprocessing.Pool, :297-306; run_dna_batch_removal_exp.py
+ * :275-287).  Replicate r is the step loop on C[rna_rows][:, dna_cols[r]]; rna_rows [m_sub] is shared (NULL = all),
+ * dna_cols [nrep, n_sub] row-major HOST int32.  Replicates are independent problems and most rounds of a solve keep
+ * only a few SMs busy, so `concurrency` of them (<= 32; 0 = 8) are kept in flight on worker streams with their own
+ * workspaces, each on a slice of the chip.  Outputs (HOST): assign [nrep, m_sub], step [nrep, m_sub],
+ * step_obj [nrep, ceil(m_sub/n_sub)] (may be NULL), cert_gap [nrep] = the replicate's largest per-step relative
+ * duality gap (may be NULL).  Every replicate is solved to optimality (and certified) like a separate
+ * mcd_subinstance_steps call: same objectives, same assignments except where exact ties (duplicated DNA cells) leave
+ * several optima -- the trajectory of the solver depends on its grid size.
+ */
+int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols,
+                          int64_t n_sub, int32_t* assign, int32_t* step, double* step_obj, double* cert_gap,
+                          int concurrency, mcd_stats* stats);
 int mcd_corr_rows(mcd_handle h, const int32_t* rows, int64_t nrows, double* out, int out_space);
 /* out[k] = C[rows[k], cols[k]] of the resident matrix (HOST indices, HOST out): the `corr_val` of a sub-instance's
  * matched pairs (run_loo_experiment.py:285). */

@@ -97,6 +97,7 @@ SIGNATURES = {
     "mcd_lap_max_certified": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP]),
     "mcd_lap_certify": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _VP]),
     "mcd_subinstance_steps": (_I, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
+    "mcd_subinstance_sweep": (_I, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)]),
     "mcd_corr_rows": (_I, [_VP, _VP, _I64, _VP, _I]),
     "mcd_corr_pairs": (_I, [_VP, _VP, _VP, _I64, _VP]),
     "mcd_null_assignments": (_I, [_VP, _I64, C.c_uint64, _VP, _VP, _I]),
@@ -286,6 +287,29 @@ class Handle:
         self.check(self.lib.mcd_subinstance_steps(self.h, _ptr(rna_rows), m, _ptr(dna_cols), n, _ptr(assign), _ptr(step),
                                                   _ptr(objs), MEM_HOST, C.byref(stats)))
         return assign, step, objs, stats
+
+    def subinstance_sweep(self, dna_cols, rna_rows=None, M=None, concurrency=8):
+        """``len(dna_cols)`` replicates of :meth:`subinstance` kept ``concurrency`` at a time in flight
+        (``mcd_subinstance_sweep``).  ``dna_cols``: int array [nrep, n_sub] of columns of the resident matrix
+        (repeats allowed).  Returns (assign [nrep, m], step [nrep, m], objs [nrep, nsteps], cert_gap [nrep], stats)."""
+        dna_cols = np.ascontiguousarray(dna_cols, dtype=np.int32)
+        if dna_cols.ndim != 2:
+            raise ValueError("dna_cols must be a 2-D array [replicates, DNA cells per replicate]")
+        nrep, n = dna_cols.shape
+        if rna_rows is not None:
+            rna_rows = np.ascontiguousarray(rna_rows, dtype=np.int32)
+            m = rna_rows.size
+        else:
+            m = int(M)
+        nsteps = self.lib.mcd_num_steps(m, n)
+        assign = np.empty((nrep, m), dtype=np.int32)
+        step = np.empty((nrep, m), dtype=np.int32)
+        objs = np.empty((nrep, nsteps), dtype=np.float64)
+        gaps = np.empty(nrep, dtype=np.float64)
+        stats = McdStats()
+        self.check(self.lib.mcd_subinstance_sweep(self.h, nrep, _ptr(rna_rows), m, _ptr(dna_cols), n, _ptr(assign),
+                                                  _ptr(step), _ptr(objs), _ptr(gaps), int(concurrency), C.byref(stats)))
+        return assign, step, objs, gaps, stats
 
     def corr_rows(self, rows, N):
         rows = np.ascontiguousarray(rows, dtype=np.int32)

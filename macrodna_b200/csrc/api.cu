@@ -93,6 +93,8 @@ int mcd_destroy(mcd_handle h) {
   if (h == nullptr) return MCD_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (mcd_context* w : h->workers) mcd_destroy(w);
+  h->workers.clear();
   for (auto& b : h->ws)
     if (b.ptr) cudaFree(b.ptr);
   for (auto ev : h->ev) cudaEventDestroy(ev);
@@ -1122,6 +1124,140 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
     stats->ms_total = ms;
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
+  }
+  return step_status(h, bad);
+}
+
+// worker k of a handle (created on first use)
+static int sweep_worker(mcd_context* h, size_t k, mcd_context** out) {
+  while (h->workers.size() <= k) {
+    mcd_context* w = new (std::nothrow) mcd_context();
+    if (w == nullptr) return mcd_fail(h, MCD_ERR_NOMEM, "worker context");
+    w->device = h->device;
+    w->sm_count = h->sm_count;
+    cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_flags, 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_flags, 0, 64, w->stream);
+    if (e != cudaSuccess) {
+      mcd_destroy(w);
+      return mcd_fail(h, MCD_ERR_CUDA, "worker context", e);
+    }
+    h->workers.push_back(w);
+  }
+  *out = h->workers[k];
+  return MCD_OK;
+}
+
+int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols,
+                          int64_t n_sub, int32_t* assign, int32_t* step, double* step_obj, double* cert_gap,
+                          int concurrency, mcd_stats* stats) {
+  if (!h) return MCD_ERR_INVALID;
+  if (!assign || !step || !dna_cols || nrep < 1 || m_sub < 1 || n_sub < 1 || h->last_M < 1 || h->last_assign == nullptr)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_sweep: no mcd_cell2cell result is resident / bad arguments");
+  if (!rna_rows && m_sub != h->last_M)
+    return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_sweep: NULL rna_rows means all rows");
+  for (int64_t i = 0; rna_rows && i < m_sub; ++i)
+    if (rna_rows[i] < 0 || rna_rows[i] >= h->last_M)
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_sweep: RNA row out of range");
+  for (int64_t j = 0; j < nrep * n_sub; ++j)
+    if (dna_cols[j] < 0 || dna_cols[j] >= h->last_N)
+      return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_sweep: DNA column out of range");
+  MCD_CUDA(h, cudaSetDevice(h->device));
+  int K = concurrency < 1 ? 8 : concurrency;
+  if (K > 32) K = 32;
+  if ((int64_t)K > nrep) K = (int)nrep;
+  const int64_t nsteps = mcd_num_steps(m_sub, n_sub);
+  const size_t rep_bytes = (step_out_bytes(m_sub, nsteps) + 255) / 256 * 256;
+  int64_t batch = (int64_t)((size_t)1 << 30) / (int64_t)rep_bytes;  // <= 1 GiB of per-replicate outputs at a time
+  if (batch < K) batch = K;
+  if (batch > nrep) batch = nrep;
+  int st;
+  void *p_idx = nullptr, *p_out = nullptr;
+  if ((st = mcd_ws(h, WS_SWEEP_IDX, (size_t)(m_sub + batch * n_sub) * 4, &p_idx))) return st;
+  if ((st = mcd_ws(h, WS_SWEEP_OUT, (size_t)batch * rep_bytes, &p_out))) return st;
+  int* d_rows = rna_rows ? static_cast<int*>(p_idx) : nullptr;
+  int* d_cols = static_cast<int*>(p_idx) + m_sub;
+  if (rna_rows) MCD_CUDA(h, cudaMemcpyAsync(d_rows, rna_rows, (size_t)m_sub * 4, cudaMemcpyHostToDevice, h->stream));
+  const int64_t lds = (n_sub + 1) & ~1LL, ldst = (m_sub + 1) & ~1LL;
+  const double* C = static_cast<const double*>(h->ws[WS_C].ptr);
+  // every worker solves on a slice of the chip: the cooperative grid of the wide rounds is capped so that K of them
+  // are co-resident (the narrow rounds run on one 8- or 16-CTA cluster per solve anyway)
+  std::vector<mcd_context*> ws((size_t)K);
+  const int total_blocks = h->sm_count * (h->opt.lap_blocks_per_sm < 1 ? 1 : h->opt.lap_blocks_per_sm);
+  for (int k = 0; k < K; ++k) {
+    if ((st = sweep_worker(h, (size_t)k, &ws[k]))) return st;
+    ws[k]->opt = h->opt;
+    ws[k]->launches = 0;
+    if (h->opt.lap_grid_blocks <= 0) {
+      int gb = total_blocks / K;
+      ws[k]->opt.lap_grid_blocks = gb < 16 ? 16 : gb;
+    }
+  }
+  const int64_t launches0 = h->launches;
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
+  std::vector<mcd_lap_counters> hc((size_t)(nsteps * batch));
+  std::vector<mcd_lap_cert> hcert((size_t)(nsteps * batch));
+  if (stats) memset(stats, 0, sizeof *stats);
+  int bad = 0;
+  for (int64_t r0 = 0; r0 < nrep; r0 += batch) {
+    const int64_t nb = nrep - r0 < batch ? nrep - r0 : batch;
+    MCD_CUDA(h, cudaMemcpyAsync(d_cols, dna_cols + r0 * n_sub, (size_t)nb * n_sub * 4, cudaMemcpyHostToDevice, h->stream));
+    MCD_CUDA(h, cudaEventRecord(get_event(h, 5), h->stream));
+    for (int k = 0; k < K; ++k) MCD_CUDA(h, cudaStreamWaitEvent(ws[k]->stream, get_event(h, 5), 0));
+    for (int64_t b = 0; b < nb; ++b) {
+      mcd_context* w = ws[(size_t)(b % K)];
+      void *pc = nullptr, *pct = nullptr;
+      if ((st = mcd_ws(w, WS_SUB_C, (size_t)m_sub * lds * 8, &pc)) || (st = mcd_ws(w, WS_SUB_CT, (size_t)n_sub * ldst * 8, &pct)))
+        return mcd_fail(h, st, "worker workspace");
+      double* subC = static_cast<double*>(pc);
+      double* subCt = static_cast<double*>(pct);
+      dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), grid_rows(m_sub));
+      gather_sub_kernel<<<grid, 256, 0, w->stream>>>(C, h->last_ldc, d_rows, d_cols + b * n_sub, m_sub, n_sub, subC, lds);
+      MCD_LAUNCH_CHECK(w, "gather_sub_kernel");
+      if ((st = mcd_transpose_f64(w, subC, m_sub, n_sub, lds, subCt, ldst))) return mcd_fail(h, st, w->err.c_str());
+      const StepOut out = carve_step_out(static_cast<char*>(p_out) + (size_t)b * rep_bytes, m_sub, nsteps);
+      if ((st = enqueue_step_loop(w, subC, lds, subCt, ldst, m_sub, n_sub, out, 0, false, false)))
+        return mcd_fail(h, st, w->err.c_str());
+    }
+    for (int k = 0; k < K; ++k) {
+      MCD_CUDA(h, cudaEventRecord(get_event(ws[k], 0), ws[k]->stream));
+      MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(ws[k], 0), 0));
+    }
+    // results of the batch: strided device block -> dense host arrays
+    const StepOut o0 = carve_step_out(p_out, m_sub, nsteps);
+    MCD_CUDA(h, cudaMemcpy2DAsync(assign + r0 * m_sub, (size_t)m_sub * 4, o0.assign, rep_bytes, (size_t)m_sub * 4, (size_t)nb,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(h, cudaMemcpy2DAsync(step + r0 * m_sub, (size_t)m_sub * 4, o0.step, rep_bytes, (size_t)m_sub * 4, (size_t)nb,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    if (step_obj)
+      MCD_CUDA(h, cudaMemcpy2DAsync(step_obj + r0 * nsteps, (size_t)nsteps * 8, o0.obj, rep_bytes, (size_t)nsteps * 8,
+                                    (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(h, cudaMemcpy2DAsync(hc.data(), sizeof(mcd_lap_counters) * nsteps, o0.cnt, rep_bytes,
+                                  sizeof(mcd_lap_counters) * nsteps, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(h, cudaMemcpy2DAsync(hcert.data(), sizeof(mcd_lap_cert) * nsteps, o0.cert, rep_bytes,
+                                  sizeof(mcd_lap_cert) * nsteps, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+    MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t b = 0; b < nb; ++b) {
+      const mcd_lap_cert* rc = hcert.data() + b * nsteps;
+      bad |= fold_step_records(h, m_sub, n_sub, nsteps, hc.data() + b * nsteps, rc, stats, 0, false);
+      if (cert_gap) {
+        double g = 0.0;
+        for (int64_t s2 = 0; s2 < nsteps; ++s2) g = rc[s2].rel_gap > g ? rc[s2].rel_gap : g;
+        cert_gap[r0 + b] = h->opt.certify ? g : -1.0;
+      }
+    }
+  }
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
+  MCD_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
+    stats->ms_lap = ms;
+    stats->ms_total = ms;
+    stats->n_steps = nsteps;
+    int64_t launches = h->launches - launches0;
+    for (int k = 0; k < K; ++k) launches += ws[k]->launches;
+    stats->kernel_launches = launches;
   }
   return step_status(h, bad);
 }

@@ -60,6 +60,9 @@ struct mcd_context {
   // shape of the last mcd_cell2cell call whose correlation matrix / assignment are still resident
   int64_t last_M = 0, last_N = 0, last_ldc = 0;
   const int* last_assign = nullptr;
+  // worker contexts of the replicate sweep (own stream + workspace each; same device): replicates are independent
+  // problems, and most rounds of a solve keep a handful of SMs busy, so several are kept in flight
+  std::vector<mcd_context*> workers;
 };
 
 enum {
@@ -83,6 +86,8 @@ enum {
   WS_SUB_CT,
   WS_SUB_IDX,
   WS_SUB_MISC,
+  WS_SWEEP_IDX,  // replicate sweep: RNA rows + the batch's DNA columns
+  WS_SWEEP_OUT,  // replicate sweep: per-replicate step-loop outputs of the batch
 };
 
 int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);

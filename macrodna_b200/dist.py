@@ -63,6 +63,11 @@ class ShardedCell2Cell:
         self.h, self.M, self.N, self.G = handle, M, N, G
         self.world, self.rank, self.device = world, rank, device
         self.precision = precision
+        if precision == "ozaki":
+            # exact int32 accumulation bounds the gene count of the integer path (as in the fused single-GPU driver)
+            nsl = int(handle.lib.mcd_ozaki_slices(handle.h, M, N, G))
+            if nsl * 4096.0 * handle.lib.mcd_padded_k_split(G) >= 2147483648.0:
+                self.precision = "fp64"
         self.lo, self.hi = row_shard(M, world, rank)
         self._bufs = None
 
@@ -87,7 +92,7 @@ class ShardedCell2Cell:
                 ops = dict(a=torch.empty((m_loc, ldk), **f64), b=torch.empty((self.N, ldk), **f64))
             elif self.precision == "ozaki":
                 ldk = lib.mcd_padded_k_split(self.G)
-                nsl = int(lib.mcd_ozaki_slices_for(self.M, self.N, self.G))
+                nsl = int(lib.mcd_ozaki_slices(self.h.h, self.M, self.N, self.G))
                 i8 = dict(dtype=torch.int8, device=self.device)
                 ops = dict(a=torch.empty((nsl, m_loc, ldk), **i8), b=torch.empty((nsl, self.N, ldk), **i8),
                            sa=torch.empty(m_loc, **f64), sb=torch.empty(self.N, **f64), nsl=nsl)
@@ -193,29 +198,44 @@ class ShardedCell2Cell:
 
 
 def sweep_assignments(handle, rna: np.ndarray, dna: np.ndarray, replicate_cols, world=1, rank=0, precision="ozaki",
-                      reuse_corr=True):
+                      reuse_corr=True, concurrency=8):
     """Resampling-stability sweep (config 4; reference
-    ``Resampling_stability_analyses/CRC_data_analyses/clonal_proportions_resampling.py:172-201``):
-    replicate r is the hot path on ``dna[replicate_cols[r]]`` (DNA cells resampled with replacement).
-    Replicas only: rank ``r mod world`` runs replicate r, no collective.
+    ``Resampling_stability_analyses/CRC_data_analyses/clonal_proportions_resampling.py:172-201``, run there under
+    ``multiprocessing.Pool(20)``, ``:297-306``): replicate r is the hot path on ``dna[replicate_cols[r]]`` (DNA cells
+    resampled with replacement).  Replicas only: rank ``r mod world`` runs replicate r, no collective.
 
     ``reuse_corr`` (declared optimisation): a replicate only gathers DNA cells and the genes are
     untouched, so its correlation matrix is a column gather of the base matrix -- the base matrix is computed once
-    per rank and every replicate runs ``mcd_subinstance_steps`` on it (same values bit for bit: the same kernel
-    computed them).  ``reuse_corr=False`` recomputes everything per replicate like the reference does.
+    per rank and the rank's replicates run as ONE ``mcd_subinstance_sweep`` call that keeps ``concurrency`` of them
+    in flight on the GPU (same values bit for bit: the same kernels compute them).  ``reuse_corr=False`` recomputes
+    everything per replicate like the reference does.
     Returns {replicate index: (assign, step, objs)} for this rank's replicates.
     """
     out = {}
     M, G = rna.shape
     mine = [r for r in range(len(replicate_cols)) if replicate_owner(r, world) == rank]
-    if reuse_corr and mine:
+    if not mine:
+        return out
+    if reuse_corr:
         handle.cell2cell(rna, dna, M, dna.shape[0], G, precision=precision)
+        by_len = {}
+        for r in mine:
+            by_len.setdefault(len(replicate_cols[r]), []).append(r)
+        for n_sub, group in by_len.items():
+            cols = np.stack([np.asarray(replicate_cols[r], dtype=np.int32) for r in group])
+            assign, step, objs, _, _ = handle.subinstance_sweep(cols, M=M, concurrency=concurrency)
+            for k, r in enumerate(group):
+                out[r] = (assign[k], step[k], objs[k])
+        return out
     for r in mine:
-        cols = np.asarray(replicate_cols[r])
-        if reuse_corr:
-            assign, step, objs, _ = handle.subinstance(None, cols, M=M, N=dna.shape[0])
-        else:
-            sub = np.ascontiguousarray(dna[cols])
-            assign, step, objs, _ = handle.cell2cell(rna, sub, M, sub.shape[0], G, precision=precision)
+        sub = np.ascontiguousarray(dna[np.asarray(replicate_cols[r])])
+        assign, step, objs, _ = handle.cell2cell(rna, sub, M, sub.shape[0], G, precision=precision)
         out[r] = (assign, step, objs)
     return out
+
+
+def replicate_accuracy(assign, cols, rna_clone, dna_clone):
+    """Per-replicate clone accuracy of the reference's sweep (clonal_proportions_resampling.py:191-201): the share of
+    RNA cells whose predicted DNA cell carries the RNA cell's own clone label.  ``assign`` holds positions in ``cols``."""
+    pred = np.asarray(dna_clone)[np.asarray(cols)[np.asarray(assign)]]
+    return float(np.mean(pred == np.asarray(rna_clone)))

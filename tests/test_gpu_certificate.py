@@ -62,7 +62,7 @@ def test_certificate_proves_the_solver_optimum(handle, shape):
 
 
 def test_certificate_catches_damage(handle):
-    """The checker is not a rubber stamp: a swapped pair, a doubly used object and a lowered price each show."""
+    """The checker is not a rubber stamp: a swapped pair, a doubly used object and wrong prices each show."""
     from scipy.optimize import linear_sum_assignment
 
     rng = np.random.default_rng(5)
@@ -83,11 +83,10 @@ def test_certificate_catches_damage(handle):
     dup = col.copy()
     dup[5] = dup[6]
     assert _certify(handle, d_w, n, m, dup, prices)[3] >= 1
-    # (c) prices that are not dual feasible for this assignment (one object made cheap): the matched edges stop being
-    #     the row maxima -> positive gap
+    # (c) prices under which the assignment is not the persons' best response (one matched object made 0.1 dearer:
+    #     its owner now prefers another object) -> positive gap
     p2 = prices.copy()
-    j = int(np.argmax(prices))
-    p2[j] = 0.0
+    p2[col[0]] += 0.1
     assert _certify(handle, d_w, n, m, col, p2)[0] > 1e-9
     # (d) SciPy's optimum with OUR prices certifies (the optimum is unique on this instance)
     r, c = linear_sum_assignment(w, maximize=True)

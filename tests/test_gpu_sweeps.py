@@ -90,3 +90,44 @@ def test_null_assignments_distribution(handle, mn):
     again = rt.assign_many(20000, seed=5)
     assert (again == sums).all()  # deterministic in (seed, trial)
     assert isinstance(rt.assign(), float)
+
+
+def test_concurrent_sweep_equals_one_at_a_time(handle):
+    """mcd_subinstance_sweep keeps several replicates in flight on worker streams (each on a slice of the chip); every
+    replicate must come out as the one-at-a-time call gives it: same objectives always, same assignments on tie-free
+    replicates (DNA cells dropped / permuted); resampled replicates (duplicated DNA cells = exact ties) are optimal
+    step by step (certificate) with equal objectives."""
+    from macrodna_b200 import dist, synth
+    from oracle import restatement as R
+
+    inst = synth.make_arrays(700, 120, 500, 4, seed=17)
+    M, N, G = 700, 120, 500
+    handle.cell2cell(inst.rna, inst.dna, M, N, G)
+    rng = np.random.default_rng(3)
+    subsets = np.stack([rng.permutation(N)[:100] for _ in range(9)]).astype(np.int32)      # tie-free
+    resampled = np.stack([synth.resample_dna_columns(inst.dna_clone, seed=s) for s in range(9)]).astype(np.int32)
+    for cols, tie_free in ((subsets, True), (resampled, False)):
+        a, s, o, gaps, st = handle.subinstance_sweep(cols, M=M, concurrency=4)
+        assert (gaps >= 0).all() and gaps.max() <= 1e-12 and st.as_dict()["cert_bad"] == 0
+        for r in range(cols.shape[0]):
+            a1, s1, o1, _ = handle.subinstance(None, cols[r], M=M, N=N)
+            assert np.allclose(o[r], o1, rtol=1e-12)
+            if tie_free:
+                assert (a[r] == a1).all() and (s[r] == s1).all()
+            assert np.bincount(s[r])[1:].sum() == M
+    # against the oracle, and the accuracy of the reference's sweep (clonal_proportions_resampling.py:191-201)
+    c_ref = R.correlation_matrix(inst.rna, inst.dna)
+    a, s, o, gaps, _ = handle.subinstance_sweep(subsets[:3], M=M, concurrency=3)
+    for r in range(3):
+        a_ref, s_ref, o_ref = R.step_loop(c_ref[:, subsets[r]])
+        assert (a[r] == a_ref).all() and (s[r] == s_ref).all() and np.allclose(o[r], o_ref, rtol=1e-12)
+        acc = dist.replicate_accuracy(a[r], subsets[r], inst.rna_clone, inst.dna_clone)
+        assert acc == np.mean(inst.dna_clone[subsets[r][a_ref]] == inst.rna_clone) and acc > 0.5
+    # the multi-rank driver: ranks own replicates r mod P, results identical to the single-rank sweep
+    whole = dist.sweep_assignments(handle, inst.rna, inst.dna, list(subsets), world=1, rank=0, concurrency=4)
+    part = {}
+    for rank in range(2):
+        part.update(dist.sweep_assignments(handle, inst.rna, inst.dna, list(subsets), world=2, rank=rank, concurrency=2))
+    assert sorted(part) == sorted(whole) == list(range(9))
+    for r in whole:
+        assert (whole[r][0] == part[r][0]).all() and (whole[r][1] == part[r][1]).all()
