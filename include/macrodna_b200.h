@@ -97,7 +97,9 @@ void* mcd_stream(mcd_handle h);
 
 /*
  * Behaviour / tuning switches of a handle (all have working defaults; nothing on the product path reads the
- * environment).  Names: "certify" (1), "debug" (0: per-step solver counters on stderr), "ozaki.slices" (0 = auto),
+ * environment).  Names: "certify" (1), "debug" (0: per-step solver counters on stderr), "corr_only" (0; 1 = the
+ * fused driver stops after the correlation matrix, which stays resident for the view calls; assign comes back
+ * as -1), "ozaki.slices" (0 = auto),
  * "ozaki.align", "ozaki.plan", "k1.generic", and the solver knobs "lap.theta", "lap.eps_min", "lap.scaling",
  * "lap.max_rounds", "lap.blocks_per_sm", "lap.grid_blocks", "lap.list_max_m", "lap.lists", "lap.list_min_nu",
  * "lap.tail_cluster", "lap.tail_mh", "lap.tail_nu", "lap.aug_nu", "lap.aug_nu_square", "lap.rank_select",
@@ -236,6 +238,12 @@ int mcd_last_match_values(mcd_handle h, double* out, int64_t M, int out_space);
  * run_dna_batch_removal_exp.py, run_loo_experiment.py:217-226 `np.delete(corrs, cell_idx, 0)`): the genes are
  * untouched, so every such replicate is an index gather of the matrix the last mcd_cell2cell call left on the
  * device.  These calls keep that matrix (and mcd_last_match_values) valid.
+ *
+ * Duplicated DNA cells: when dna_cols repeats a cell (resampling WITH replacement, clonal_proportions_resampling.py
+ * :184-187) the replicate has exact ties by construction and any of the tied optima answers the reference's ILP.
+ * The copies of a cell are handled as a class of similar persons of the auction (they never bid against each
+ * other; their duals are equalised before the certificate), so such replicates solve -- exactly -- as fast as
+ * tie-free ones.
  *
  * mcd_subinstance_steps: the step loop (macrodna.py:110-145) on C[rna_rows][:, dna_cols].
  *   rna_rows [m_sub], dna_cols [n_sub]: HOST int32 indices into the resident matrix (NULL = all, in order;

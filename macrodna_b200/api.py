@@ -44,6 +44,22 @@ def get_handle(device: int = 0) -> "_lib.Handle":
     return h
 
 
+class _StatsDict:
+    """Merged stats of a two-call run, with the ``as_dict`` / attribute access of ``_lib.McdStats``."""
+
+    def __init__(self, d):
+        self._d = d
+
+    def as_dict(self):
+        return dict(self._d)
+
+    def __getattr__(self, k):
+        try:
+            return self._d[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+
 class MaCroDNA:
     """B200 drop-in for the reference class (``macrodna.py:10``).
 
@@ -134,6 +150,22 @@ class MaCroDNA:
         return dna_index[keep], dna_pos, rna_pos
 
     @staticmethod
+    def _duplicate_dna_cells(dna_cells, dna_np):
+        """Duplicated DNA cell ids WITH identical data (a frame built by ``dna.loc[:, resampled_names]``).  Returns
+        (row of the first copy of every distinct cell, for every column the position of its cell among those) or None."""
+        first = {}
+        for k, c in enumerate(dna_cells):
+            first.setdefault(c, k)
+        if len(first) == len(dna_cells):
+            return None
+        first_pos = np.array([first[c] for c in dna_cells])
+        if not np.array_equal(dna_np, dna_np[first_pos]):
+            return None  # same label, different data: genuinely different cells
+        uniq = np.array(sorted(first.values()))
+        rank = {k: r for r, k in enumerate(uniq.tolist())}
+        return uniq, np.array([rank[k] for k in first_pos.tolist()], dtype=np.int32)
+
+    @staticmethod
     def _cells_by_genes(df):
         """macrodna.py:93-94 -- ``df.T.to_numpy()`` as C-contiguous float64 (cells x all genes of the frame).
         For a single-dtype float64 frame this is a zero-copy view of the frame's block."""
@@ -171,8 +203,34 @@ class MaCroDNA:
             print(q, r)
             print("MaCroDNA will be run for %s steps" % (q + (1 if r else 0)))
         h = get_handle(self.device)
-        assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, ld_rna=rna_np.shape[1], ld_dna=dna_np.shape[1],
-                                                precision=self.precision, rna_gene_idx=rna_pos, dna_gene_idx=dna_pos)
+        dup_cols = self._duplicate_dna_cells(dna_cells, dna_np)
+        if dup_cols is not None:
+            # A resampled DNA frame (`dna.loc[:, names]` with names drawn WITH replacement,
+            # clonal_proportions_resampling.py:184-190): the correlation matrix is computed on the distinct cells and
+            # the step loop runs on its column gather (exact ties between the copies are broken deterministically,
+            # see mcd_subinstance_steps in include/macrodna_b200.h).
+            uniq, cols = dup_cols
+            dna_u = np.ascontiguousarray(dna_np[uniq])
+            h.set_option("corr_only", 1)
+            try:
+                _, _, _, stats = h.cell2cell(rna_np, dna_u, M, len(uniq), G, ld_rna=rna_np.shape[1],
+                                             ld_dna=dna_u.shape[1], precision=self.precision, rna_gene_idx=rna_pos,
+                                             dna_gene_idx=dna_pos)
+            finally:
+                h.set_option("corr_only", 0)
+            assign, step, objs, stats2 = h.subinstance(None, cols, M=M, N=len(uniq))
+            d = stats.as_dict()
+            d2 = stats2.as_dict()
+            for k in ("ms_lap", "lap_rounds", "lap_bids", "lap_bytes", "lap_aug_rows", "lap_aug_steps", "cert_rel_gap",
+                      "cert_max_violation", "cert_bad", "cert_steps", "step_rounds", "step_bids", "step_cert_gap", "n_steps"):
+                d[k] = d2[k]
+            d["ms_total"] += d2["ms_total"]
+            d["kernel_launches"] += d2["kernel_launches"]
+            stats = _StatsDict(d)
+        else:
+            assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, ld_rna=rna_np.shape[1],
+                                                    ld_dna=dna_np.shape[1], precision=self.precision,
+                                                    rna_gene_idx=rna_pos, dna_gene_idx=dna_pos)
         # macrodna.py:90-91: from now on the frames are the gene-filtered ones (materialised on first access)
         if not self._rna_filtered or not self._dna_filtered or self._genes is None:
             self._genes = genes
@@ -181,10 +239,15 @@ class MaCroDNA:
         self.last_assign, self.last_step, self.last_objective = assign, step, objs
         self.last_stats = stats.as_dict()
         # the correlation matrix of THIS run stays on the device until the handle's next cell2cell call
-        h.resident_token = self._resident_token = object()
-        self._resident_shape = (M, N)
-        self._resident_cells = (rna_cells, dna_cells)
-        self.last_corr_val = h.last_match_values(M) if self.keep_corr_val else None
+        if dup_cols is None:
+            h.resident_token = self._resident_token = object()
+            self._resident_shape = (M, N)
+            self._resident_cells = (rna_cells, dna_cells)
+            self.last_corr_val = h.last_match_values(M) if self.keep_corr_val else None
+        else:
+            self._resident_token = None  # the resident matrix is the distinct-cell one: later views recompute
+            self.last_corr_val = (h.corr_pairs(np.arange(M, dtype=np.int32), dup_cols[1][assign])
+                                  if self.keep_corr_val else None)
         if self.verbose:
             for o in objs:
                 print("Obj: %g" % o)

@@ -1,6 +1,7 @@
 // C ABI of the hot path (include/macrodna_b200.h): context, workspace, step loop (K4), fused driver.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstddef>
 #include <cstring>
 #include <new>
@@ -168,6 +169,7 @@ struct OptEntry {
 const OptEntry kOptions[] = {
     MCD_OPT_I("certify", certify),
     MCD_OPT_I("debug", debug),
+    MCD_OPT_I("corr_only", corr_only),
     MCD_OPT_I("ozaki.slices", ozaki_slices),
     MCD_OPT_I("ozaki.align", ozaki_align),
     MCD_OPT_I("ozaki.plan", ozaki_plan),
@@ -482,6 +484,26 @@ __global__ void gather_pairs_kernel(const double* __restrict__ C, int64_t ldc, c
   if (k < n) out[k] = C[(int64_t)rows[k] * ldc + cols[k]];
 }
 
+// cls[j] = first position of cols that holds the same cell as position j (copies of a cell share an id < n); returns
+// the number of extra copies.  O(n log n).
+int64_t duplicate_classes(const int32_t* cols, int64_t n, std::vector<int>& cls) {
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t j = 0; j < n; ++j) order[(size_t)j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cols[a] < cols[b]; });
+  cls.assign((size_t)n, 0);
+  int64_t extra = 0;
+  for (int64_t q = 0; q < n; ++q) {
+    const int64_t j = order[(size_t)q];
+    if (q > 0 && cols[j] == cols[order[(size_t)q - 1]]) {
+      cls[(size_t)j] = cls[(size_t)order[(size_t)q - 1]];
+      ++extra;
+    } else {
+      cls[(size_t)j] = (int)j;
+    }
+  }
+  return extra;
+}
+
 // rows of a gather go to gridDim.y, which the hardware caps at 65535: the kernels loop over the rest
 inline unsigned grid_rows(int64_t rows) { return (unsigned)(rows < 65535 ? (rows < 1 ? 1 : rows) : 65535); }
 
@@ -600,8 +622,11 @@ int step_status(mcd_context* h, int bad) {
 // Enqueue the whole step loop on h->stream (no host synchronisation: every step's shape is known
 // up front because each non-final step matches exactly N RNA cells).
 // Device outputs: d_assign[M], d_step[M], d_obj[nsteps], d_counters[nsteps].
+// dna_class: optional DEVICE int [N], equal ids = DNA cells that are copies of one another (identical columns of C):
+// in the steps where the DNA cells are the solver's persons they bid as a class (see mcd_launch_lap).
 int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double* Ct, int64_t ldct, int64_t M,
-                      int64_t N, const StepOut& out, size_t ev_base, bool check_finite, bool record_events = true) {
+                      int64_t N, const StepOut& out, size_t ev_base, bool check_finite, bool record_events = true,
+                      const int* dna_class = nullptr) {
   int* d_assign = out.assign;
   int* d_step = out.step;
   double* d_obj = out.obj;
@@ -645,7 +670,7 @@ int enqueue_step_loop(mcd_context* h, const double* C, int64_t ldc, const double
         Wp = W;
       }
       if ((st = mcd_launch_lap(h, Wp, N, R, ldw, col4row, d_obj + s, lapbuf, d_counters + s, check_finite && s == 0,
-                               out.cert + s)))
+                               out.cert + s, nullptr, dna_class)))
         return st;
       record_dna_major_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(col4row, (int)N, act[cur], d_assign,
                                                                                  d_step, flag, (int)(s + 1));
@@ -956,7 +981,15 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   void* misc = nullptr;
   if ((st = mcd_ws(h, WS_MISC, step_out_bytes(M, nsteps), &misc))) return st;
   const StepOut out = carve_step_out(misc, M, nsteps);
-  if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, out, EV_LAP, false))) return st;
+  if (h->opt.corr_only) {
+    // the caller only wants the correlation matrix resident (it will solve views of it): no step loop
+    MCD_CUDA(h, cudaMemsetAsync(misc, 0, step_out_bytes(M, nsteps), h->stream));
+    MCD_CUDA(h, cudaMemsetAsync(out.assign, 0xFF, (size_t)M * 4, h->stream));
+    for (size_t e = 0; e <= (size_t)(nsteps < MCD_MAX_STEP_STATS ? nsteps : MCD_MAX_STEP_STATS); ++e)
+      MCD_CUDA(h, cudaEventRecord(get_event(h, EV_LAP + e), h->stream));
+  } else if ((st = enqueue_step_loop(h, C, ldc, Ct, ldct, M, N, out, EV_LAP, false))) {
+    return st;
+  }
   MCD_CUDA(h, cudaEventRecord(get_event(h, EV_LAPEND), h->stream));
 
   // ---- outputs
@@ -978,7 +1011,7 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
 
   if (stats) memset(stats, 0, sizeof *stats);
-  const int bad = fold_step_records(h, M, N, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
+  const int bad = h->opt.corr_only ? 0 : fold_step_records(h, M, N, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
   if (stats) {
     auto el = [&](int a, int b) {
       float ms = 0.f;
@@ -1084,11 +1117,19 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
   void *pc = nullptr, *pct = nullptr, *pi = nullptr, *misc = nullptr;
   if ((st = mcd_ws(h, WS_SUB_C, (size_t)m_sub * lds * 8, &pc))) return st;
   if ((st = mcd_ws(h, WS_SUB_CT, (size_t)n_sub * ldst * 8, &pct))) return st;
-  if ((st = mcd_ws(h, WS_SUB_IDX, (size_t)(m_sub + n_sub) * 4, &pi))) return st;
+  if ((st = mcd_ws(h, WS_SUB_IDX, (size_t)(m_sub + 2 * n_sub) * 4, &pi))) return st;
   int* d_rows = rna_rows ? static_cast<int*>(pi) : nullptr;
   int* d_cols = dna_cols ? static_cast<int*>(pi) + m_sub : nullptr;
+  int* d_cls = nullptr;
   if (rna_rows) MCD_CUDA(h, cudaMemcpyAsync(d_rows, rna_rows, (size_t)m_sub * 4, cudaMemcpyHostToDevice, h->stream));
   if (dna_cols) MCD_CUDA(h, cudaMemcpyAsync(d_cols, dna_cols, (size_t)n_sub * 4, cudaMemcpyHostToDevice, h->stream));
+  // copies of a DNA cell (resampling with replacement): identical columns, i.e. exact ties by construction.  They
+  // are told to the solver as classes of similar persons.
+  std::vector<int> cls;
+  if (dna_cols && duplicate_classes(dna_cols, n_sub, cls) > 0) {
+    d_cls = static_cast<int*>(pi) + m_sub + n_sub;
+    MCD_CUDA(h, cudaMemcpyAsync(d_cls, cls.data(), (size_t)n_sub * 4, cudaMemcpyHostToDevice, h->stream));
+  }
   const int64_t launches0 = h->launches;
   const size_t EV_LAP = 8;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
@@ -1104,7 +1145,7 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
   const int64_t nsteps = mcd_num_steps(m_sub, n_sub);
   if ((st = mcd_ws(h, WS_SUB_MISC, step_out_bytes(m_sub, nsteps), &misc))) return st;
   const StepOut out = carve_step_out(misc, m_sub, nsteps);
-  if ((st = enqueue_step_loop(h, subC, lds, subCt, ldst, m_sub, n_sub, out, EV_LAP, false))) return st;
+  if ((st = enqueue_step_loop(h, subC, lds, subCt, ldst, m_sub, n_sub, out, EV_LAP, false, true, d_cls))) return st;
   MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
   const cudaMemcpyKind kind = out_space == MCD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   MCD_CUDA(h, cudaMemcpyAsync(assign, out.assign, (size_t)m_sub * 4, kind, h->stream));
@@ -1173,10 +1214,13 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
   if (batch > nrep) batch = nrep;
   int st;
   void *p_idx = nullptr, *p_out = nullptr;
-  if ((st = mcd_ws(h, WS_SWEEP_IDX, (size_t)(m_sub + batch * n_sub) * 4, &p_idx))) return st;
+  if ((st = mcd_ws(h, WS_SWEEP_IDX, (size_t)(m_sub + 2 * batch * n_sub) * 4, &p_idx))) return st;
   if ((st = mcd_ws(h, WS_SWEEP_OUT, (size_t)batch * rep_bytes, &p_out))) return st;
   int* d_rows = rna_rows ? static_cast<int*>(p_idx) : nullptr;
   int* d_cols = static_cast<int*>(p_idx) + m_sub;
+  int* d_clss = d_cols + batch * n_sub;
+  std::vector<int> clss((size_t)(batch * n_sub)), cls1;
+  std::vector<int64_t> n_extra((size_t)batch);
   if (rna_rows) MCD_CUDA(h, cudaMemcpyAsync(d_rows, rna_rows, (size_t)m_sub * 4, cudaMemcpyHostToDevice, h->stream));
   const int64_t lds = (n_sub + 1) & ~1LL, ldst = (m_sub + 1) & ~1LL;
   const double* C = static_cast<const double*>(h->ws[WS_C].ptr);
@@ -1202,6 +1246,11 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
   for (int64_t r0 = 0; r0 < nrep; r0 += batch) {
     const int64_t nb = nrep - r0 < batch ? nrep - r0 : batch;
     MCD_CUDA(h, cudaMemcpyAsync(d_cols, dna_cols + r0 * n_sub, (size_t)nb * n_sub * 4, cudaMemcpyHostToDevice, h->stream));
+    for (int64_t b = 0; b < nb; ++b) {
+      n_extra[(size_t)b] = duplicate_classes(dna_cols + (r0 + b) * n_sub, n_sub, cls1);
+      std::copy(cls1.begin(), cls1.end(), clss.begin() + b * n_sub);
+    }
+    MCD_CUDA(h, cudaMemcpyAsync(d_clss, clss.data(), (size_t)nb * n_sub * 4, cudaMemcpyHostToDevice, h->stream));
     MCD_CUDA(h, cudaEventRecord(get_event(h, 5), h->stream));
     for (int k = 0; k < K; ++k) MCD_CUDA(h, cudaStreamWaitEvent(ws[k]->stream, get_event(h, 5), 0));
     for (int64_t b = 0; b < nb; ++b) {
@@ -1216,7 +1265,8 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
       MCD_LAUNCH_CHECK(w, "gather_sub_kernel");
       if ((st = mcd_transpose_f64(w, subC, m_sub, n_sub, lds, subCt, ldst))) return mcd_fail(h, st, w->err.c_str());
       const StepOut out = carve_step_out(static_cast<char*>(p_out) + (size_t)b * rep_bytes, m_sub, nsteps);
-      if ((st = enqueue_step_loop(w, subC, lds, subCt, ldst, m_sub, n_sub, out, 0, false, false)))
+      if ((st = enqueue_step_loop(w, subC, lds, subCt, ldst, m_sub, n_sub, out, 0, false, false,
+                                  n_extra[(size_t)b] > 0 ? d_clss + b * n_sub : nullptr)))
         return mcd_fail(h, st, w->err.c_str());
     }
     for (int k = 0; k < K; ++k) {

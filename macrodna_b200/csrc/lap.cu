@@ -50,6 +50,12 @@ constexpr int CAND_T = 4;          // per-thread candidates kept during a row sw
 constexpr int MAX_PHASES = 48;
 constexpr int MAX_GRID_SLOTS = 4096;  // >= cooperative grid size
 constexpr double NEG_INF = -1.0e300;  // finite sentinel: inputs are finite correlations
+// A bid on an OWNED object must raise its price by more than this to be applied (2^-46: costs are correlations, O(1),
+// so this is ~60 ulps of a price).  Exact ties (duplicated cells) give increments of 0 or of a few ulps of rounding
+// noise; the latter used to count as progress, and two tied persons could swap an object back and forth until the
+// round guard (264 000 rounds on a resampled replicate).  Treated as "no increment", such bidders stall and go to the
+// shortest-augmenting-path kernel, which is exact from any dual-feasible state.
+constexpr double GAMMA_TIE = 1.4210854715202004e-14;
 
 // Grid-wide barrier for the persistent wide kernel (launched with cudaLaunchCooperativeKernel so
 // all CTAs are co-resident).  One monotonic counter; each CTA's thread 0 arrives with a RELEASE
@@ -145,6 +151,14 @@ struct LapState {
   mcd_lap_counters* counters;
   const int* flags;  // [0] != 0: non-finite data was seen upstream -> every solver kernel is a no-op
   long long max_rounds;
+  // Classes of similar persons (identical cost rows: copies of one resampled DNA cell).  pcls[i] = class id of
+  // person i (persons with equal ids are copies), NULL = every person is its own class; ocls[j] = class of the
+  // person that owns object j (-1 = free).  A bidder never bids against its own copies: objects held by its class
+  // are skipped (swapping two copies changes nothing, and a bid between them has increment exactly 0 -- the auction
+  // would stall on every duplicated cell).  What this leaves open -- copies holding objects at different profit
+  // levels -- is closed by lap_class_equalize_kernel before the augmentation kernel / the certificate.
+  const int* pcls;
+  int* ocls;
 };
 
 struct Top2 {
@@ -243,6 +257,7 @@ __device__ __forceinline__ unsigned long long pack_bid(double gamma, int person)
 template <bool COHERENT>
 __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top2& out) {
   const int K = s.list_k;
+  const int mycls = s.pcls != nullptr ? __ldg(s.pcls + i) : -2;  // -2 never equals an owner class (>= -1)
   const int* lj = s.lj + (int64_t)i * LIST_K;
   const double* lw = s.lw + (int64_t)i * LIST_K;
   // everything that depends only on i is requested up front: the bid is two dependent memory latencies
@@ -265,14 +280,19 @@ __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top
   out = t;
   if (!valid) return false;  // never built: the slots hold garbage, do not touch them
   double ps[LIST_K / 32];
+  int oc[LIST_K / 32];
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q) {
     ps[q] = 0.0;
-    if (js[q] >= 0) ps[q] = COHERENT ? ldm(s.price + js[q]) : s.price[js[q]];
+    oc[q] = -1;
+    if (js[q] >= 0) {
+      ps[q] = COHERENT ? ldm(s.price + js[q]) : s.price[js[q]];
+      if (s.pcls != nullptr) oc[q] = COHERENT ? ldm(s.ocls + js[q]) : s.ocls[js[q]];  // same latency as the price
+    }
   }
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q)
-    if (js[q] >= 0) top2_push(t, ws[q] - ps[q], js[q]);
+    if (js[q] >= 0 && oc[q] != mycls) top2_push(t, ws[q] - ps[q], js[q]);  // objects of the bidder's own copies: skipped
   t = top2_warp_reduce(t);
   out = t;
   if (K == s.m) return true;  // every object is listed
@@ -820,6 +840,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
     if (first_phase) s.price[j] = 0.0;
     s.owner[j] = -1;
     s.key[j] = 0ull;
+    if (s.pcls != nullptr) s.ocls[j] = -1;
   }
   for (int i = gtid; i < s.n; i += gthreads) {
     s.col4row[i] = -1;
@@ -1025,12 +1046,13 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       bool requeue = true;
       if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
         const double p_new = p_old + gam;
-        if (prev < 0 || p_new > p_old) {
+        if (prev < 0 || gam > GAMMA_TIE) {
           if (prev >= 0) {
             s.col4row[prev] = -1;
             nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = prev;
           }
           s.owner[j] = i;
+          if (s.pcls != nullptr) s.ocls[j] = __ldg(s.pcls + i);
           s.col4row[i] = j;
           s.price[j] = p_new;
           // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
@@ -1201,7 +1223,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState
     const int nfail = s_cnt[0];
     for (int f = 0; f < nfail; ++f) {
       const int b = s_fail[f];
-      const Top2 t = full_scan_build<TAIL_THREADS, false>(s, s_list[cur][b], cand_v, cand_j, red);
+      Top2 t = full_scan_build<TAIL_THREADS, false>(s, s_list[cur][b], cand_v, cand_j, red);
+      if (s.pcls != nullptr) {  // the scan does not know the classes of similar persons: bid from the fresh list
+        __syncthreads();
+        if (warp == 0) list_bid<false>(s, s_list[cur][b], lane, t);
+      }
       if (tid == 0) finalize(b, t);
     }
     sweeps += nfail;
@@ -1222,10 +1248,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState
         const double p_old = s.price[j];
         const double p_new = p_old + s_gam[tid];
         const int prev = s.owner[j];
-        if (prev < 0 || p_new > p_old) {
+        if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
           applied = true;
           person_out = prev;  // the evicted owner (or -1) bids next round
           s.owner[j] = i;
+          if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
           s.price[j] = p_new;
           s.col4row[i] = j;
           s.profit[i] = (s_bval[tid] + p_old) - p_new;
@@ -1557,7 +1584,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
       for (int q = 0; q < nu; ++q)
         if (s_bj[q] == j && s_bkey[q] > key) win = false;
       const double p_new = p_old + gamma;
-      const bool applied = win && (prev < 0 || p_new > p_old);
+      const bool applied = win && (prev < 0 || gamma > GAMMA_TIE);
       const bool has = live && (applied ? prev >= 0 : true);
       const int person_out = applied ? prev : i;
       const unsigned hmask = __ballot_sync(0xffffffffu, has);
@@ -1939,10 +1966,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
             const double p_old = s.price[j];
             const double p_new = p_old + s_gam[lane];
             const int prev = s.owner[j];
-            if (prev < 0 || p_new > p_old) {
+            if (prev < 0 || s_gam[lane] > GAMMA_TIE) {
               applied = true;
               person_out = prev;  // the evicted owner (or -1) bids next round
               s.owner[j] = i;
+              if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
               s.price[j] = p_new;
               s.col4row[i] = j;
               s.profit[i] = (s_bval[lane] + p_old) - p_new;
@@ -2229,6 +2257,39 @@ __global__ void __launch_bounds__(1024) lap_objective_kernel(const double* __res
 
 
 // ------------------------------------------------------------------------------------------------
+// Classes of similar persons, closing step.  During the auction a person ignores the objects its own copies hold,
+// so copies may sit at different profit levels: pi_A > pi_B for two copies A, B of one cell means B would prefer A's
+// object -- harmless for the ASSIGNMENT (A and B are interchangeable) but not a dual-feasible point.  Raising the
+// price of every copy's object until its profit equals the lowest profit of the class,
+//     p[c(i)] <- W[i, c(i)] - min_{k in class(i)} (W[k, c(k)] - p[c(k)]),
+// restores exact complementary slackness for everybody: the copy at the lowest level was at its best response
+// against every object outside the class; the class's objects are now tight at that level; other persons only see
+// prices rise on objects they do not hold; unassigned objects keep price 0.  (This is the bid of a similarity class
+// in the auction for transportation problems, Bertsekas & Castanon 1989, applied once at the end.)  One CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lap_class_equalize_kernel(LapState s) {
+  if (s.pcls == nullptr || s.flags[0]) return;
+  unsigned long long* level = reinterpret_cast<unsigned long long*>(s.bval);  // [n] scratch: class id < n
+  const int tid = threadIdx.x;
+  for (int i = tid; i < s.n; i += 1024) level[i] = ~0ull;
+  __syncthreads();
+  for (int i = tid; i < s.n; i += 1024) {
+    const int c = s.col4row[i];
+    if (c >= 0) atomicMin(level + s.pcls[i], f64_sortable(s.W[(int64_t)i * s.ldw + c] - s.price[c]));
+  }
+  __syncthreads();
+  for (int i = tid; i < s.n; i += 1024) {
+    const int c = s.col4row[i];
+    if (c < 0) continue;
+    const double w = s.W[(int64_t)i * s.ldw + c];
+    const double lvl = sortable_f64(level[s.pcls[i]]);
+    const double pnew = w - lvl;
+    if (pnew > s.price[c]) s.price[c] = pnew;
+    s.profit[i] = w - s.price[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Dual certificate of one solve -- independent of HOW the assignment was found.
 // Inputs: the cost block W, the assignment col4row and the object prices the solver ended with.  With
 //   lambda = min price over the assigned objects,  q_j = max(price_j - lambda, 0) >= 0,  u_i = max_j (W_ij - q_j),
@@ -2377,12 +2438,13 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up(m * 4, 256);            // pred
   b += align_up((n + 1) * 4, 256);      // sc_col
   b += align_up((n + 1) * 8, 256);      // sc_val
+  b += align_up(m * 4, 256);            // ocls
   return b;
 }
 
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
                    double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite,
-                   mcd_lap_cert* d_cert, double* prices_out) {
+                   mcd_lap_cert* d_cert, double* prices_out, const int* person_class) {
   if (n <= 0) return MCD_OK;
   if (n > m) return mcd_fail(h, MCD_ERR_INVALID, "lap: rows must be the smaller side");
   if (m > 0x3fffffff) return mcd_fail(h, MCD_ERR_UNSUPPORTED, "lap: too many objects");
@@ -2431,6 +2493,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.pred = reinterpret_cast<int*>(take(m * 4));
   s.sc_col = reinterpret_cast<int*>(take((n + 1) * 4));
   s.sc_val = reinterpret_cast<double*>(take((n + 1) * 8));
+  s.ocls = reinterpret_cast<int*>(take(m * 4));
+  s.pcls = (n < m) ? person_class : nullptr;  // classes ride on the candidate-list bids, which only n < m uses
   s.col4row = col4row;
   s.counters = d_counters;
   s.flags = h->d_flags;
@@ -2540,6 +2604,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
         MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_cluster_kernel, s, mc));
       h->launches++;
     }
+  }
+  if (s.pcls != nullptr) {
+    lap_class_equalize_kernel<<<1, 1024, 0, h->stream>>>(s);
+    MCD_LAUNCH_CHECK(h, "lap_class_equalize_kernel");
   }
   lap_augment_kernel<<<1, JV_THREADS, 0, h->stream>>>(s);
   MCD_LAUNCH_CHECK(h, "lap_augment_kernel");

@@ -18,6 +18,7 @@ struct mcd_buffer {
 struct mcd_options {
   int certify = 1;            // "certify": dual certificate sweep after every assignment solve
   int debug = 0;              // "debug": per-step solver counters on stderr
+  int corr_only = 0;          // "corr_only": mcd_cell2cell stops after K2 (matrix resident for the view calls)
   int ozaki_slices = 0;       // "ozaki.slices": 0 = automatic (mcd_ozaki_slices_for)
   int ozaki_align = 1;        // "ozaki.align": wave alignment of the K2c producers
   int ozaki_plan = 1;         // "ozaki.plan": unit order of a K2c pass
@@ -163,10 +164,11 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m);
 // check_finite: also scan W for NaN/Inf (raises the context's non-finite flag; the solver kernels then no-op)
 // d_cert: optional; when non-NULL (and the handle's "certify" option is on) the dual certificate of the solve is
 // written there and a failed certificate raises d_counters->status bit 1.  prices_out: optional [m] device copy of
-// the final object prices.
+// the final object prices.  person_class: optional DEVICE int [n], ids in [0, n), equal ids = persons with identical
+// cost rows (copies of one resampled cell): they bid as a class of similar persons (lap.cu, LapState::pcls).
 int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, int32_t* col4row,
                    double* objective, void* work, mcd_lap_counters* d_counters, bool check_finite,
-                   mcd_lap_cert* d_cert = nullptr, double* prices_out = nullptr);
+                   mcd_lap_cert* d_cert = nullptr, double* prices_out = nullptr, const int* person_class = nullptr);
 // certificate of an arbitrary (col4row, prices) pair; work: >= 4 m + 8 n + 1024 bytes of device scratch
 int mcd_launch_lap_certify(mcd_context* h, const double* W, int64_t n, int64_t m, int64_t ldw, const int32_t* col4row,
                            const double* prices, void* work, mcd_lap_cert* d_cert, mcd_lap_counters* d_counters);

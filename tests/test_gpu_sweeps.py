@@ -131,3 +131,45 @@ def test_concurrent_sweep_equals_one_at_a_time(handle):
     assert sorted(part) == sorted(whole) == list(range(9))
     for r in whole:
         assert (whole[r][0] == part[r][0]).all() and (whole[r][1] == part[r][1]).all()
+
+
+def test_resampled_replicates_with_duplicated_cells(handle):
+    """Resampling WITH replacement (clonal_proportions_resampling.py:184-187) duplicates DNA cells: exact ties by
+    construction.  Round 1 spun to the round guard on them (264 000 rounds, seconds per replicate).  The copies of a
+    cell now bid as a class of similar persons; every step must be optimal (SciPy on the oracle matrix, objective
+    within 1e-12), carry a certificate at rounding level, and need about as many rounds as a tie-free instance."""
+    from macrodna_b200 import MaCroDNA, synth
+    from oracle import restatement as R
+    from scipy.optimize import linear_sum_assignment
+
+    inst = synth.make_arrays(1500, 300, 800, 4, seed=31)
+    M, N, G = 1500, 300, 800
+    _, _, _, base = handle.cell2cell(inst.rna, inst.dna, M, N, G)
+    base_rounds = base.as_dict()["lap_rounds"]
+    c_ref = R.correlation_matrix(inst.rna, inst.dna)
+    for seed in range(3):
+        cols = synth.resample_dna_columns(inst.dna_clone, seed=seed).astype(np.int32)
+        assert len(set(cols.tolist())) < 0.8 * N  # plenty of duplicates
+        a, s, o, st = handle.subinstance(None, cols, M=M, N=N)
+        d = st.as_dict()
+        assert d["lap_rounds"] < 6 * base_rounds, (d["lap_rounds"], base_rounds)
+        assert 0.0 <= d["cert_rel_gap"] <= 1e-12 and d["cert_bad"] == 0
+        sub = c_ref[:, cols]
+        remaining = np.arange(M)
+        for k in range(5):
+            rows = np.flatnonzero(s == k + 1)
+            r, c = linear_sum_assignment(sub[remaining], maximize=True)
+            best = sub[remaining][r, c].sum()
+            mine = sub[rows, a[rows]].sum()
+            assert abs(mine - best) <= 1e-12 * abs(best), (seed, k, mine, best)
+            assert abs(o[k] - mine) <= 1e-12 * abs(mine)
+            assert len(set(a[rows].tolist())) == len(rows)         # injective within the step
+            remaining = np.setdiff1d(remaining, rows)
+    # the drop-in class on a resampled FRAME (duplicate column labels, identical data): same machinery
+    rna_df, dna_df, lab = synth.make_frames(inst)
+    names = [dna_df.columns[j] for j in cols]
+    m = MaCroDNA(rna_df, dna_df.loc[:, names], variant="resampling")
+    frame = m.cell2cell_assignment()
+    assert list(frame.columns) == ["predicted_dna_cell", "rna_cell", "step"] and len(frame) == M
+    assert m.last_stats["cert_rel_gap"] <= 1e-12 and m.last_stats["lap_rounds"] < 6 * base_rounds
+    assert np.allclose(m.last_objective, o, rtol=1e-12)
