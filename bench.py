@@ -412,7 +412,8 @@ def sweep_block(torch, h, world, rank, device, args, barrier):
            "accuracy": {"mean": acc_sum / nrep, "min": acc_min, "max": acc_max,
                         "definition": "share of RNA cells whose predicted DNA cell has their clone "
                                       "(clonal_proportions_resampling.py:191-201)"},
-           "cert_rel_gap_max": gap, "kernel_launches": int(st.as_dict()["kernel_launches"])}
+           "cert_rel_gap_max": gap, "kernel_launches": int(st.as_dict()["kernel_launches"]),
+           "replicates_resolved_without_classes": int(st.as_dict()["sweep_fallbacks"])}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         import multiprocessing as mp
 

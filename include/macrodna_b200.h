@@ -80,6 +80,8 @@ typedef struct {
   int64_t cert_bad;          /* unassigned persons + doubly used objects found by the checker (0)     */
   int64_t cert_steps;        /* steps certified                                                       */
   double step_cert_gap[MCD_MAX_STEP_STATS]; /* per-step relative gap (-1: not certified)              */
+  int64_t sweep_fallbacks;   /* mcd_subinstance_sweep: replicates re-solved without the class treatment of
+                                duplicated cells because their certificate failed with it             */
 } mcd_stats;
 
 int mcd_abi_version(void);

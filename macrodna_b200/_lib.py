@@ -50,6 +50,7 @@ class McdStats(C.Structure):
         ("cert_bad", C.c_int64),
         ("cert_steps", C.c_int64),
         ("step_cert_gap", C.c_double * MAX_STEP_STATS),
+        ("sweep_fallbacks", C.c_int64),
     ]
 
     def as_dict(self):
@@ -59,7 +60,7 @@ class McdStats(C.Structure):
         d["step_ms"] = [self.step_ms[i] for i in range(n)]
         d["step_rounds"] = [self.step_rounds[i] for i in range(n)]
         d["step_bids"] = [self.step_bids[i] for i in range(n)]
-        for k in ("cert_rel_gap", "cert_max_violation", "cert_bad", "cert_steps"):
+        for k in ("cert_rel_gap", "cert_max_violation", "cert_bad", "cert_steps", "sweep_fallbacks"):
             d[k] = getattr(self, k)
         d["step_cert_gap"] = [self.step_cert_gap[i] for i in range(n)]
         return d

@@ -1098,8 +1098,27 @@ int mcd_corr_pairs(mcd_handle h, const int32_t* rows, const int32_t* cols, int64
   return MCD_OK;
 }
 
+static int subinstance_steps_impl(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols,
+                                  int64_t n_sub, int32_t* assign, int32_t* step, double* step_obj, int out_space,
+                                  mcd_stats* stats, bool use_classes, int* bad_out);
+
 int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols, int64_t n_sub,
                           int32_t* assign, int32_t* step, double* step_obj, int out_space, mcd_stats* stats) {
+  int bad = 0;
+  int st = subinstance_steps_impl(h, rna_rows, m_sub, dna_cols, n_sub, assign, step, step_obj, out_space, stats, true, &bad);
+  if (st == MCD_ERR_NOT_CONVERGED && (bad & 4)) {
+    // The class treatment of duplicated cells leaves one window open (two copies settling at different levels in the
+    // very round a third party buys the dearer copy's object); the certificate catches it.  Such a replicate is
+    // solved again with every copy as a person of its own: exact ties then stall the auction and the
+    // augmenting-path kernel finishes them -- slower, never wrong.
+    st = subinstance_steps_impl(h, rna_rows, m_sub, dna_cols, n_sub, assign, step, step_obj, out_space, stats, false, &bad);
+  }
+  return st;
+}
+
+static int subinstance_steps_impl(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, const int32_t* dna_cols,
+                                  int64_t n_sub, int32_t* assign, int32_t* step, double* step_obj, int out_space,
+                                  mcd_stats* stats, bool use_classes, int* bad_out) {
   if (!h) return MCD_ERR_INVALID;
   if (!assign || !step || m_sub < 1 || n_sub < 1 || h->last_M < 1 || h->last_assign == nullptr)
     return mcd_fail(h, MCD_ERR_INVALID, "mcd_subinstance_steps: no mcd_cell2cell result is resident");
@@ -1126,7 +1145,7 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
   // copies of a DNA cell (resampling with replacement): identical columns, i.e. exact ties by construction.  They
   // are told to the solver as classes of similar persons.
   std::vector<int> cls;
-  if (dna_cols && duplicate_classes(dna_cols, n_sub, cls) > 0) {
+  if (use_classes && dna_cols && duplicate_classes(dna_cols, n_sub, cls) > 0) {
     d_cls = static_cast<int*>(pi) + m_sub + n_sub;
     MCD_CUDA(h, cudaMemcpyAsync(d_cls, cls.data(), (size_t)n_sub * 4, cudaMemcpyHostToDevice, h->stream));
   }
@@ -1166,6 +1185,7 @@ int mcd_subinstance_steps(mcd_handle h, const int32_t* rna_rows, int64_t m_sub, 
     stats->n_steps = nsteps;
     stats->kernel_launches = h->launches - launches0;
   }
+  if (bad_out) *bad_out = bad | ((bad & 2) && d_cls != nullptr ? 4 : 0);  // bit 2: certificate failed WITH classes in use
   return step_status(h, bad);
 }
 
@@ -1289,12 +1309,24 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
     MCD_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int64_t b = 0; b < nb; ++b) {
       const mcd_lap_cert* rc = hcert.data() + b * nsteps;
-      bad |= fold_step_records(h, m_sub, n_sub, nsteps, hc.data() + b * nsteps, rc, stats, 0, false);
-      if (cert_gap) {
-        double g = 0.0;
-        for (int64_t s2 = 0; s2 < nsteps; ++s2) g = rc[s2].rel_gap > g ? rc[s2].rel_gap : g;
-        cert_gap[r0 + b] = h->opt.certify ? g : -1.0;
+      int bad_b = fold_step_records(h, m_sub, n_sub, nsteps, hc.data() + b * nsteps, rc, stats, 0, false);
+      double g = 0.0;
+      for (int64_t s2 = 0; s2 < nsteps; ++s2) g = rc[s2].rel_gap > g ? rc[s2].rel_gap : g;
+      if ((bad_b & 2) && n_extra[(size_t)b] > 0) {
+        // certificate failed with the class treatment of duplicated cells: solve this replicate again without it
+        // (see mcd_subinstance_steps)
+        mcd_stats st2;
+        const int r = (int)(r0 + b);
+        const int rc2 = subinstance_steps_impl(h, rna_rows, m_sub, dna_cols + (int64_t)r * n_sub, n_sub,
+                                               assign + (int64_t)r * m_sub, step + (int64_t)r * m_sub,
+                                               step_obj ? step_obj + (int64_t)r * nsteps : nullptr, MCD_MEM_HOST, &st2, false,
+                                               &bad_b);
+        if (rc2 != MCD_OK && rc2 != MCD_ERR_NOT_CONVERGED) return rc2;
+        g = st2.cert_rel_gap;
+        if (stats) stats->sweep_fallbacks += 1;
       }
+      bad |= bad_b;
+      if (cert_gap) cert_gap[r0 + b] = h->opt.certify ? g : -1.0;
     }
   }
   MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));

@@ -157,8 +157,13 @@ struct LapState {
   // are skipped (swapping two copies changes nothing, and a bid between them has increment exactly 0 -- the auction
   // would stall on every duplicated cell).  What this leaves open -- copies holding objects at different profit
   // levels -- is closed by lap_class_equalize_kernel before the augmentation kernel / the certificate.
+  //   clevel[t] = lowest profit any member of class t has settled at so far (order-preserving key).  While copies sit
+  //   at different levels, an object held by a copy at a HIGH level is under-priced from the class's point of view
+  //   (a copy at the low level would rather have it): a bidder of another class must raise its price at least to the
+  //   class level to take it, otherwise the owner raises it there itself and keeps it (class_defends()).
   const int* pcls;
   int* ocls;
+  unsigned long long* clevel;
 };
 
 struct Top2 {
@@ -297,6 +302,23 @@ __device__ __forceinline__ bool list_bid(const LapState& s, int i, int lane, Top
   out = t;
   if (K == s.m) return true;  // every object is listed
   return t.j2 >= 0 && t.v2 >= b;
+}
+
+// A winning bid (increment gam) of person i on object j held by `prev`: if prev's class has settled lower than
+// prev's own profit by more than gam, the object changes hands too cheaply -- a copy of prev at the class level would
+// still prefer it at the new price, and nobody would ever tell it.  Returns the amount the owner must raise the price
+// by to defend the object (> gam), or 0 when the bid stands.  COHERENT as in list_bid.
+template <bool COHERENT>
+__device__ __forceinline__ double class_defends(const LapState& s, int i, int prev, double gam) {
+  if (s.pcls == nullptr || prev < 0) return 0.0;
+  const int tp = __ldg(s.pcls + prev);
+  if (tp == __ldg(s.pcls + i)) return 0.0;
+  const double lvl = sortable_f64(ldm(s.clevel + tp));  // written by atomics (L2): never through a stale L1 line
+  const double need = (COHERENT ? ldm(s.profit + prev) : s.profit[prev]) - lvl;
+  return need > gam ? need : 0.0;
+}
+__device__ __forceinline__ void class_settle(const LapState& s, int i, double profit) {
+  if (s.pcls != nullptr) atomicMin(s.clevel + __ldg(s.pcls + i), f64_sortable(profit));
 }
 
 // Whole-row sweep by an NT-thread CTA: exact top-2 of W[i,:] - price, and the person's new candidate
@@ -850,6 +872,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       s.lvalid[i] = 0;
     else if (s.lvalid[i] != 0)
       s.lvalid[i] = 1;  // round stamps of the previous launch (see the bidding stage) -> plain "valid"
+    if (s.pcls != nullptr) s.clevel[i] = ~0ull;
   }
   if (gtid == 0) {
     ctrl->cnt[0] = s.n;
@@ -1046,7 +1069,13 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       bool requeue = true;
       if ((unsigned)(kj & 0xffffffffull) == (unsigned)(i + 1)) {
         const double p_new = p_old + gam;
-        if (prev < 0 || gam > GAMMA_TIE) {
+        const double defend = class_defends<true>(s, i, prev, gam);
+        if (defend > 0.0) {
+          // the owner's class has settled lower: the owner raises the price to the class level and keeps the object
+          s.price[j] = p_old + defend;
+          s.profit[prev] = ldm(s.profit + prev) - defend;
+          atomicAdd(&ctrl->progress[parity], 1);
+        } else if (prev < 0 || gam > GAMMA_TIE) {
           if (prev >= 0) {
             s.col4row[prev] = -1;
             nxt[atomicAdd(&ctrl->cnt[cur ^ 1], 1)] = prev;
@@ -1058,7 +1087,9 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
           // profit := value of the owned object at its new price.  bval = fl(W - p_old) from the scan;
           // (bval + p_old) - p_new reproduces W - p_new to rounding, keeping the matched edge tight
           // at the 1-ulp level without re-reading W.
-          s.profit[i] = (bval + p_old) - p_new;
+          const double prof = (bval + p_old) - p_new;
+          s.profit[i] = prof;
+          class_settle(s, i, prof);
           atomicAdd(&ctrl->progress[parity], 1);
           requeue = false;
         }
@@ -1248,14 +1279,21 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_list_kernel(LapState
         const double p_old = s.price[j];
         const double p_new = p_old + s_gam[tid];
         const int prev = s.owner[j];
-        if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
+        const double defend = class_defends<false>(s, i, prev, s_gam[tid]);
+        if (defend > 0.0) {  // the owner's class has settled lower: the owner raises the price and keeps the object
+          s.price[j] = p_old + defend;
+          s.profit[prev] -= defend;
+          applied = true;  // (progress; the bidder is re-queued: person_out stays i)
+        } else if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
           applied = true;
           person_out = prev;  // the evicted owner (or -1) bids next round
           s.owner[j] = i;
           if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
           s.price[j] = p_new;
           s.col4row[i] = j;
-          s.profit[i] = (s_bval[tid] + p_old) - p_new;
+          const double prof = (s_bval[tid] + p_old) - p_new;
+          s.profit[i] = prof;
+          class_settle(s, i, prof);
           if (prev >= 0) s.col4row[prev] = -1;
         }
       }
@@ -1966,14 +2004,21 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
             const double p_old = s.price[j];
             const double p_new = p_old + s_gam[lane];
             const int prev = s.owner[j];
-            if (prev < 0 || s_gam[lane] > GAMMA_TIE) {
+            const double defend = class_defends<false>(s, i, prev, s_gam[lane]);
+            if (defend > 0.0) {  // the owner's class has settled lower: the owner raises the price and keeps the object
+              s.price[j] = p_old + defend;
+              s.profit[prev] -= defend;
+              applied = true;  // (progress; the bidder is re-queued: person_out stays i)
+            } else if (prev < 0 || s_gam[lane] > GAMMA_TIE) {
               applied = true;
               person_out = prev;  // the evicted owner (or -1) bids next round
               s.owner[j] = i;
               if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
               s.price[j] = p_new;
               s.col4row[i] = j;
-              s.profit[i] = (s_bval[lane] + p_old) - p_new;
+              const double prof = (s_bval[lane] + p_old) - p_new;
+              s.profit[i] = prof;
+              class_settle(s, i, prof);
               if (prev >= 0) s.col4row[prev] = -1;
             }
           }
@@ -2439,6 +2484,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up((n + 1) * 4, 256);      // sc_col
   b += align_up((n + 1) * 8, 256);      // sc_val
   b += align_up(m * 4, 256);            // ocls
+  b += align_up(n * 8, 256);            // clevel
   return b;
 }
 
@@ -2494,6 +2540,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.sc_col = reinterpret_cast<int*>(take((n + 1) * 4));
   s.sc_val = reinterpret_cast<double*>(take((n + 1) * 8));
   s.ocls = reinterpret_cast<int*>(take(m * 4));
+  s.clevel = reinterpret_cast<unsigned long long*>(take(n * 8));
   s.pcls = (n < m) ? person_class : nullptr;  // classes ride on the candidate-list bids, which only n < m uses
   s.col4row = col4row;
   s.counters = d_counters;

@@ -41,7 +41,7 @@ def test_pure_host_entry_points():
     assert lib.mcd_padded_k_split(6) == 64
     assert [lib.mcd_num_steps(m, n) for m, n in [(9, 4), (3, 7), (5, 5), (8, 4), (5, 1)]] == [3, 1, 1, 2, 5]
     assert lib.mcd_strerror(0) == b"ok" and b"non-finite" in lib.mcd_strerror(-4)
-    assert ctypes.sizeof(_lib.McdStats) == 8 * (13 + 8 + 3 * 64 + 4 + 64)
+    assert ctypes.sizeof(_lib.McdStats) == 8 * (13 + 8 + 3 * 64 + 4 + 64 + 1)
 
 
 def _frames(m=5, n=3, g=8):
