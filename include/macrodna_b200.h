@@ -227,6 +227,17 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
                          double* corr_out, int out_space, mcd_stats* stats);
 
 /*
+ * The fused driver on several GPUs of one node, one caller (HOST inputs and outputs; gene indices as in
+ * mcd_cell2cell_gather, NULL = identity).  hs[0..ndev): one handle per device.  RNA rows are sharded: device d
+ * standardises rows [d*ceil(M/ndev), ...) and the DNA operand and contracts its row block -- no exchange inside the
+ * contraction --, the correlation shards go to hs[0]'s device by peer copies (NVLink), which runs the step loop.
+ * The matrix stays resident on hs[0] for the view calls.  Results are bit-identical to the single-device call.
+ */
+int mcd_cell2cell_multi(mcd_handle* hs, int ndev, const double* rna, int64_t ld_rna, const int32_t* rna_gene_idx,
+                        const double* dna, int64_t ld_dna, const int32_t* dna_gene_idx, int64_t M, int64_t N, int64_t G,
+                        int precision, int32_t* assign, int32_t* step, double* step_obj, mcd_stats* stats);
+
+/*
  * Matched correlation of every RNA cell, corr[i, assign[i]], of the LAST mcd_cell2cell call on this handle
  * (its correlation matrix is still resident).  This is the `corr_val` column of the leave-one-out variant
  * (Resampling_stability_analyses/BE_data_analyses/run_loo_experiment.py:194) and the operand of the median

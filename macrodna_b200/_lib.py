@@ -107,6 +107,10 @@ SIGNATURES = {
         _I,
         [_VP, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)],
     ),
+    "mcd_cell2cell_multi": (
+        _I,
+        [C.POINTER(_VP), _I, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I64, _I64, _I, _VP, _VP, _VP, C.POINTER(McdStats)],
+    ),
     "mcd_cell2cell": (
         _I,
         [_VP, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _I, _I, _VP, _VP, _VP, _VP, _I, C.POINTER(McdStats)],
@@ -169,6 +173,34 @@ def _out(x, n, dtype, name):
             raise ValueError("macrodna_b200: %s must be a writable C-contiguous %s array of at least %d elements" % (
                 name, np.dtype(dtype).name, n))
     return x
+
+
+def cell2cell_multi(handles, rna, dna, M, N, G, ld_rna=None, ld_dna=None, precision="ozaki", rna_gene_idx=None,
+                    dna_gene_idx=None):
+    """The hot path on several GPUs of one node from one process (``mcd_cell2cell_multi``): RNA rows sharded over
+    ``handles`` (one per device), step loop on ``handles[0]``, where the correlation matrix stays resident."""
+    h0 = handles[0]
+    for h in handles:
+        h.resident_token = None
+    nsteps = h0.lib.mcd_num_steps(M, N)
+    rna = _matrix(rna, M, ld_rna or G, "rna")
+    dna = _matrix(dna, N, ld_dna or G, "dna")
+    if not isinstance(rna, np.ndarray) or not isinstance(dna, np.ndarray):
+        raise ValueError("macrodna_b200: the multi-GPU driver takes host arrays")
+    assign = np.empty(M, dtype=np.int32)
+    step = np.empty(M, dtype=np.int32)
+    step_obj = np.empty(nsteps, dtype=np.float64)
+    if rna_gene_idx is not None:
+        rna_gene_idx = np.ascontiguousarray(rna_gene_idx, dtype=np.int32)
+    if dna_gene_idx is not None:
+        dna_gene_idx = np.ascontiguousarray(dna_gene_idx, dtype=np.int32)
+    stats = McdStats()
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    st = h0.lib.mcd_cell2cell_multi(arr, len(handles), _ptr(rna), ld_rna or G, _ptr(rna_gene_idx), _ptr(dna), ld_dna or G,
+                                    _ptr(dna_gene_idx), M, N, G, PREC[precision], _ptr(assign), _ptr(step), _ptr(step_obj),
+                                    C.byref(stats))
+    h0.check(st)
+    return assign, step, step_obj, stats
 
 
 class Handle:

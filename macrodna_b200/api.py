@@ -21,7 +21,7 @@ from . import _lib
 _HANDLES = {}
 
 
-def get_handle(device: int = 0) -> "_lib.Handle":
+def get_handle(device: int = 0, slot: int = 0) -> "_lib.Handle":
     """Per-process, per-device library context (created on first use, so instances pickle).
 
     The reference's sweep scripts run the class in the parent and then fork a ``multiprocessing.Pool``
@@ -29,7 +29,8 @@ def get_handle(device: int = 0) -> "_lib.Handle":
     inherited from another process is never touched.  A child that inherited one is told how to run instead
     (CUDA cannot be re-initialised in a forked child); a child of a parent that had not used the GPU yet simply
     creates its own context."""
-    h = _HANDLES.get(device)
+    key = device if slot == 0 else (device, slot)  # slot > 0: a further context on the same device (devices=[0, 0])
+    h = _HANDLES.get(key)
     if h is not None and getattr(h, "pid", None) != os.getpid():
         # inherited over fork(): the parent had already initialised CUDA in this address space
         raise RuntimeError(
@@ -40,8 +41,19 @@ def get_handle(device: int = 0) -> "_lib.Handle":
             "flight on the GPU." % (h.pid,))
     if h is None or h.h is None:
         h = _lib.Handle(device)
-        _HANDLES[device] = h
+        _HANDLES[key] = h
     return h
+
+
+def get_handles(devices) -> list:
+    """One context per entry of ``devices`` (a device may be listed more than once: separate contexts on it)."""
+    seen = {}
+    out = []
+    for d in devices:
+        d = int(d)
+        out.append(get_handle(d, seen.get(d, 0)))
+        seen[d] = seen.get(d, 0) + 1
+    return out
 
 
 class _StatsDict:
@@ -67,6 +79,8 @@ class MaCroDNA:
     frames (index = gene ids, columns = cell ids, ``:13``); ``dna_label`` has columns
     ``clone`` and ``cell`` (``:14``).  Keyword-only extras default to reference behaviour:
 
+    * ``devices``: list of CUDA devices of this node; more than one shards the correlation work by RNA rows
+      (``mcd_cell2cell_multi``), results identical to one device;
     * ``precision``: ``"ozaki"`` (default: FP64-equivalent correlations from the int8 tcgen05 tensor cores, exact
       digit-slice products, ~1e-12 absolute), ``"fp64"`` (FP64 tensor pipe, DMMA) or ``"split"`` (tcgen05 fp16
       hi/lo split precision, ~3e-7 absolute);
@@ -82,13 +96,16 @@ class MaCroDNA:
       ``predicted_dna_cell, rna_cell, step`` and no index (clonal_proportions_resampling.py:166-169).
     """
 
-    def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, precision="ozaki",
+    def __init__(self, rna_df=None, dna_df=None, dna_label=None, *, device=0, devices=None, precision="ozaki",
                  clone_column="predict_clone", verbose=False, variant="src"):
         self._genes = None  # shared genes of the last run: the frames below are filtered lazily (see rna_df)
         self.rna_df = rna_df
         self.dna_df = dna_df
         self.dna_label = dna_label
-        self.device = device
+        # devices=[d0, d1, ...]: the RNA rows are sharded over these GPUs for standardisation + correlation (no exchange
+        # inside the contraction), the shards meet on d0 over NVLink and d0 runs the step loop (mcd_cell2cell_multi)
+        self.devices = [int(d) for d in devices] if devices is not None else None
+        self.device = self.devices[0] if self.devices else device
         self.precision = precision
         self.clone_column = clone_column
         self.verbose = verbose
@@ -227,6 +244,11 @@ class MaCroDNA:
             d["ms_total"] += d2["ms_total"]
             d["kernel_launches"] += d2["kernel_launches"]
             stats = _StatsDict(d)
+        elif self.devices and len(self.devices) > 1:
+            assign, step, objs, stats = _lib.cell2cell_multi(get_handles(self.devices), rna_np, dna_np, M, N, G,
+                                                             ld_rna=rna_np.shape[1], ld_dna=dna_np.shape[1],
+                                                             precision=self.precision, rna_gene_idx=rna_pos,
+                                                             dna_gene_idx=dna_pos)
         else:
             assign, step, objs, stats = h.cell2cell(rna_np, dna_np, M, N, G, ld_rna=rna_np.shape[1],
                                                     ld_dna=dna_np.shape[1], precision=self.precision,

@@ -103,6 +103,7 @@ int mcd_destroy(mcd_handle h) {
     if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
+  if (h->stager) mcd_stager_destroy(h->stager);
   if (h->d_flags) cudaFree(h->d_flags);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -877,6 +878,7 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   const double* d_dna = dna;
   int64_t ldr = ld_rna, ldd = ld_dna;
   int nchunk = 1;
+  bool pageable_in = false;
   // gene gather indices (device copies); with a gather the staged rows keep all ld columns of the host block
   const int* d_ridx = nullptr;
   const int* d_didx = nullptr;
@@ -899,8 +901,13 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
     void *pr = nullptr, *pd = nullptr;
     if ((st = mcd_ws(h, WS_RNA_IN, (size_t)M * wr * 8, &pr))) return st;
     if ((st = mcd_ws(h, WS_DNA_IN, (size_t)N * wd * 8, &pd))) return st;
-    MCD_CUDA(h, cudaMemcpy2DAsync(pd, (size_t)wd * 8, dna, (size_t)ld_dna * 8, (size_t)wd * 8, (size_t)N,
-                                  cudaMemcpyHostToDevice, h->stream));
+    pageable_in = mcd_is_pageable(rna) || mcd_is_pageable(dna);
+    if (pageable_in) {
+      if ((st = mcd_staged_h2d(h, static_cast<double*>(pd), wd, dna, ld_dna, wd, N, h->stream))) return st;
+    } else {
+      MCD_CUDA(h, cudaMemcpy2DAsync(pd, (size_t)wd * 8, dna, (size_t)ld_dna * 8, (size_t)wd * 8, (size_t)N,
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
     d_rna = static_cast<const double*>(pr);
     d_dna = static_cast<const double*>(pd);
     ldr = wr;
@@ -938,8 +945,12 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
     const int c = nchunk_used;
     if (in_space == MCD_MEM_HOST) {
       double* dst = const_cast<double*>(d_rna) + r0 * wr;
-      MCD_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)wr * 8, rna + r0 * ld_rna, (size_t)ld_rna * 8, (size_t)wr * 8,
-                                    (size_t)mr, cudaMemcpyHostToDevice, h->copy_stream));
+      if (pageable_in) {
+        if ((st = mcd_staged_h2d(h, dst, wr, rna + r0 * ld_rna, ld_rna, wr, mr, h->copy_stream))) return st;
+      } else {
+        MCD_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)wr * 8, rna + r0 * ld_rna, (size_t)ld_rna * 8, (size_t)wr * 8,
+                                      (size_t)mr, cudaMemcpyHostToDevice, h->copy_stream));
+      }
       MCD_CUDA(h, cudaEventRecord(get_event(h, EV_CHUNK + 4 * c), h->copy_stream));
       MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(h, EV_CHUNK + 4 * c), 0));
     } else {
@@ -1041,6 +1052,219 @@ int mcd_cell2cell_gather(mcd_handle h, const double* rna, int64_t ld_rna, const 
   h->last_N = N;
   h->last_ldc = ldc;
   h->last_assign = out.assign;
+  return MCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs, one caller.  SURVEY.md section 8e: K1 + K2 shard by RNA rows with no exchange inside the contraction;
+// the correlation shards travel once to the first device (peer copies over NVLink), which runs the step loop.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ShardOperands {
+  void* pa = nullptr;
+  void* pb = nullptr;
+  double* sA = nullptr;
+  double* sB = nullptr;
+  double* nA = nullptr;
+  double* nB = nullptr;
+};
+
+// K1 of both operands + K2 of `rows` RNA rows on handle h; C_loc [rows, ldc] (no transpose).  All on h->stream.
+int shard_standardize_correlate(mcd_context* h, const double* d_rna, int64_t ldr, const int* d_ridx, const double* d_dna,
+                                int64_t ldd, const int* d_didx, int64_t rows, int64_t N, int64_t G, int precision, int nsl,
+                                double* C_loc, int64_t ldc) {
+  int st;
+  ShardOperands o;
+  void *pnA = nullptr, *pnB = nullptr;
+  const int64_t ldk = precision == MCD_PREC_FP64 ? mcd_padded_k(G) : mcd_padded_k_split(G);
+  if ((st = mcd_ws(h, WS_NORM_A, (size_t)(rows > 0 ? rows : 1) * 8, &pnA))) return st;
+  if ((st = mcd_ws(h, WS_NORM_B, (size_t)N * 8, &pnB))) return st;
+  o.nA = static_cast<double*>(pnA);
+  o.nB = static_cast<double*>(pnB);
+  const int64_t mr = rows > 0 ? rows : 1;
+  if (precision == MCD_PREC_FP64) {
+    if ((st = mcd_ws(h, WS_RNA_C, (size_t)mr * ldk * 8, &o.pa))) return st;
+    if ((st = mcd_ws(h, WS_DNA_C, (size_t)N * ldk * 8, &o.pb))) return st;
+    if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, (double*)o.pb, ldk, nullptr, nullptr, 0, o.nB, d_didx))) return st;
+    if (rows > 0) {
+      if ((st = mcd_launch_standardize(h, d_rna, rows, G, ldr, (double*)o.pa, ldk, nullptr, nullptr, 0, o.nA, d_ridx))) return st;
+      st = mcd_launch_corr_fp64(h, (double*)o.pa, rows, (double*)o.pb, N, ldk, o.nA, o.nB, C_loc, ldc, nullptr, 0);
+    }
+  } else if (precision == MCD_PREC_OZAKI_INT8) {
+    void* ps = nullptr;
+    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)nsl * mr * ldk, &o.pa))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)nsl * N * ldk, &o.pb))) return st;
+    if ((st = mcd_ws(h, WS_SCALE, (size_t)(mr + N) * 8, &ps))) return st;
+    o.sA = static_cast<double*>(ps);
+    o.sB = o.sA + mr;
+    mcd_ozaki_out oza, ozb;
+    ozb.digits = static_cast<int8_t*>(o.pb);
+    ozb.ldk8 = ldk;
+    ozb.slice_stride = N * ldk;
+    ozb.nsl = nsl;
+    ozb.scale = o.sB;
+    oza = ozb;
+    oza.digits = static_cast<int8_t*>(o.pa);
+    oza.slice_stride = mr * ldk;
+    oza.scale = o.sA;
+    if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, nullptr, nullptr, 0, o.nB, d_didx, &ozb))) return st;
+    if (rows > 0) {
+      if ((st = mcd_launch_standardize(h, d_rna, rows, G, ldr, nullptr, 0, nullptr, nullptr, 0, o.nA, d_ridx, &oza))) return st;
+      st = mcd_launch_corr_ozaki(h, oza.digits, oza.slice_stride, rows, ozb.digits, ozb.slice_stride, N, ldk, nsl, o.sA, o.sB,
+                                 o.nA, o.nB, C_loc, ldc, nullptr, 0);
+    }
+  } else {
+    if ((st = mcd_ws(h, WS_SLICES_A, (size_t)2 * mr * ldk * 2, &o.pa))) return st;
+    if ((st = mcd_ws(h, WS_SLICES_B, (size_t)2 * N * ldk * 2, &o.pb))) return st;
+    uint16_t* a_hi = static_cast<uint16_t*>(o.pa);
+    uint16_t* b_hi = static_cast<uint16_t*>(o.pb);
+    if ((st = mcd_launch_standardize(h, d_dna, N, G, ldd, nullptr, 0, b_hi, b_hi + N * ldk, ldk, o.nB, d_didx))) return st;
+    if (rows > 0) {
+      if ((st = mcd_launch_standardize(h, d_rna, rows, G, ldr, nullptr, 0, a_hi, a_hi + mr * ldk, ldk, o.nA, d_ridx))) return st;
+      st = mcd_launch_corr_split(h, a_hi, a_hi + mr * ldk, rows, b_hi, b_hi + N * ldk, N, ldk, o.nA, o.nB, C_loc, ldc, nullptr, 0);
+    }
+  }
+  return st;
+}
+}  // namespace
+
+int mcd_cell2cell_multi(mcd_handle* hs, int ndev, const double* rna, int64_t ld_rna, const int32_t* rna_gene_idx,
+                        const double* dna, int64_t ld_dna, const int32_t* dna_gene_idx, int64_t M, int64_t N, int64_t G,
+                        int precision, int32_t* assign, int32_t* step, double* step_obj, mcd_stats* stats) {
+  if (!hs || ndev < 1 || !hs[0]) return MCD_ERR_INVALID;
+  mcd_context* h0 = hs[0];
+  if (ndev == 1)
+    return mcd_cell2cell_gather(h0, rna, ld_rna, rna_gene_idx, dna, ld_dna, dna_gene_idx, M, N, G, MCD_MEM_HOST, precision,
+                                assign, step, step_obj, nullptr, MCD_MEM_HOST, stats);
+  for (int d = 0; d < ndev; ++d)
+    if (!hs[d]) return mcd_fail(h0, MCD_ERR_INVALID, "mcd_cell2cell_multi: NULL handle");
+  if (!rna || !dna || !assign || !step || M < 1 || N < 1 || G < 1 || (!rna_gene_idx && ld_rna < G) ||
+      (!dna_gene_idx && ld_dna < G) || M > 0x3fffffff || N > 0x3fffffff || G > 0x7fffffff)
+    return mcd_fail(h0, MCD_ERR_INVALID, "mcd_cell2cell_multi arguments");
+  if (precision != MCD_PREC_FP64 && precision != MCD_PREC_SPLIT_FP16 && precision != MCD_PREC_OZAKI_INT8)
+    return mcd_fail(h0, MCD_ERR_INVALID, "unknown precision");
+  for (int64_t g = 0; g < G; ++g)
+    if ((rna_gene_idx && (rna_gene_idx[g] < 0 || rna_gene_idx[g] >= ld_rna)) ||
+        (dna_gene_idx && (dna_gene_idx[g] < 0 || dna_gene_idx[g] >= ld_dna)))
+      return mcd_fail(h0, MCD_ERR_INVALID, "mcd_cell2cell_multi: gene index out of range");
+  const int nsl = mcd_ozaki_slices(h0, M, N, G);
+  if (precision == MCD_PREC_OZAKI_INT8 && (double)nsl * 4096.0 * (double)mcd_padded_k_split(G) >= 2147483648.0)
+    precision = MCD_PREC_FP64;
+  h0->last_M = 0;
+  h0->last_assign = nullptr;
+  const int64_t ldc = (N + 1) & ~1LL, ldct = (M + 1) & ~1LL;
+  const int64_t per = (M + ndev - 1) / ndev;
+  const int64_t wr = rna_gene_idx ? ld_rna : G, wd = dna_gene_idx ? ld_dna : G;
+  int st;
+  // the whole matrix lives on the first device
+  MCD_CUDA(h0, cudaSetDevice(h0->device));
+  void *pC = nullptr, *pCt = nullptr;
+  if ((st = mcd_ws(h0, WS_C, (size_t)M * ldc * 8, &pC))) return st;
+  if ((st = mcd_ws(h0, WS_CT, (size_t)N * ldct * 8, &pCt))) return st;
+  double* C = static_cast<double*>(pC);
+  double* Ct = static_cast<double*>(pCt);
+  const int64_t launches0 = h0->launches;
+  MCD_CUDA(h0, cudaEventRecord(get_event(h0, 0), h0->stream));
+  for (int d = 0; d < ndev; ++d) {
+    mcd_context* h = hs[d];
+    const int64_t lo = d * per < M ? d * per : M, hi = lo + per < M ? lo + per : M;
+    const int64_t rows = hi - lo;
+    MCD_CUDA(h0, cudaSetDevice(h->device));
+    if (d > 0) {
+      int can = 0;
+      if (h->device != h0->device && cudaDeviceCanAccessPeer(&can, h->device, h0->device) == cudaSuccess && can) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(h0->device, 0);
+        if (pe != cudaSuccess) cudaGetLastError();  // already enabled
+      }
+    }
+    void *pr = nullptr, *pd = nullptr, *pg = nullptr, *pcl = nullptr;
+    if ((st = mcd_ws(h, WS_RNA_IN, (size_t)(rows > 0 ? rows : 1) * wr * 8, &pr))) return mcd_fail(h0, st, h->err.c_str());
+    if ((st = mcd_ws(h, WS_DNA_IN, (size_t)N * wd * 8, &pd))) return mcd_fail(h0, st, h->err.c_str());
+    const int* d_ridx = nullptr;
+    const int* d_didx = nullptr;
+    if (rna_gene_idx || dna_gene_idx) {
+      if ((st = mcd_ws(h, WS_GIDX, (size_t)2 * G * 4, &pg))) return mcd_fail(h0, st, h->err.c_str());
+      int* gi = static_cast<int*>(pg);
+      if (rna_gene_idx) {
+        MCD_CUDA(h0, cudaMemcpyAsync(gi, rna_gene_idx, (size_t)G * 4, cudaMemcpyHostToDevice, h->stream));
+        d_ridx = gi;
+      }
+      if (dna_gene_idx) {
+        MCD_CUDA(h0, cudaMemcpyAsync(gi + G, dna_gene_idx, (size_t)G * 4, cudaMemcpyHostToDevice, h->stream));
+        d_didx = gi + G;
+      }
+    }
+    // every device copies its RNA rows and the (small) DNA operand over its own PCIe link
+    MCD_CUDA(h0, cudaMemcpy2DAsync(pd, (size_t)wd * 8, dna, (size_t)ld_dna * 8, (size_t)wd * 8, (size_t)N,
+                                   cudaMemcpyHostToDevice, h->stream));
+    if (rows > 0)
+      MCD_CUDA(h0, cudaMemcpy2DAsync(pr, (size_t)wr * 8, rna + lo * ld_rna, (size_t)ld_rna * 8, (size_t)wr * 8, (size_t)rows,
+                                     cudaMemcpyHostToDevice, h->stream));
+    double* C_loc = C + lo * ldc;  // device 0 writes its shard in place
+    if (d > 0) {
+      if ((st = mcd_ws(h, WS_C, (size_t)(rows > 0 ? rows : 1) * ldc * 8, &pcl))) return mcd_fail(h0, st, h->err.c_str());
+      C_loc = static_cast<double*>(pcl);
+    } else {
+      MCD_CUDA(h0, cudaStreamWaitEvent(h->stream, get_event(h0, 0), 0));
+    }
+    if ((st = shard_standardize_correlate(h, static_cast<const double*>(pr), wr, d_ridx, static_cast<const double*>(pd), wd,
+                                          d_didx, rows, N, G, precision, nsl, C_loc, ldc)))
+      return mcd_fail(h0, st, h->err.c_str());
+    if (d > 0 && rows > 0)
+      MCD_CUDA(h0, cudaMemcpyPeerAsync(C + lo * ldc, h0->device, C_loc, h->device, (size_t)rows * ldc * 8, h->stream));
+    if (d > 0) MCD_CUDA(h0, cudaEventRecord(get_event(h, 0), h->stream));
+  }
+  MCD_CUDA(h0, cudaSetDevice(h0->device));
+  for (int d = 1; d < ndev; ++d) MCD_CUDA(h0, cudaStreamWaitEvent(h0->stream, get_event(hs[d], 0), 0));
+  MCD_CUDA(h0, cudaEventRecord(get_event(h0, 3), h0->stream));
+  if ((st = mcd_transpose_f64(h0, C, M, N, ldc, Ct, ldct))) return st;
+  const int64_t nsteps = mcd_num_steps(M, N);
+  void* misc = nullptr;
+  if ((st = mcd_ws(h0, WS_MISC, step_out_bytes(M, nsteps), &misc))) return st;
+  const StepOut out = carve_step_out(misc, M, nsteps);
+  const size_t EV_LAP = 8;
+  if ((st = enqueue_step_loop(h0, C, ldc, Ct, ldct, M, N, out, EV_LAP, false))) return st;
+  MCD_CUDA(h0, cudaEventRecord(get_event(h0, 4), h0->stream));
+  MCD_CUDA(h0, cudaMemcpyAsync(assign, out.assign, (size_t)M * 4, cudaMemcpyDeviceToHost, h0->stream));
+  MCD_CUDA(h0, cudaMemcpyAsync(step, out.step, (size_t)M * 4, cudaMemcpyDeviceToHost, h0->stream));
+  if (step_obj) MCD_CUDA(h0, cudaMemcpyAsync(step_obj, out.obj, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, h0->stream));
+  std::vector<mcd_lap_counters> hc((size_t)nsteps);
+  std::vector<mcd_lap_cert> hcert((size_t)nsteps);
+  MCD_CUDA(h0, cudaMemcpyAsync(hc.data(), out.cnt, sizeof(mcd_lap_counters) * nsteps, cudaMemcpyDeviceToHost, h0->stream));
+  MCD_CUDA(h0, cudaMemcpyAsync(hcert.data(), out.cert, sizeof(mcd_lap_cert) * nsteps, cudaMemcpyDeviceToHost, h0->stream));
+  MCD_CUDA(h0, cudaEventRecord(get_event(h0, 5), h0->stream));
+  MCD_CUDA(h0, cudaStreamSynchronize(h0->stream));
+  int flag = 0;
+  for (int d = 0; d < ndev; ++d) {  // non-finite input is flagged by K1 on the device that saw it
+    int f = 0;
+    MCD_CUDA(h0, cudaSetDevice(hs[d]->device));
+    MCD_CUDA(h0, cudaMemcpy(&f, hs[d]->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    MCD_CUDA(h0, cudaMemset(hs[d]->d_flags, 0, sizeof(int)));
+    flag |= f;
+  }
+  MCD_CUDA(h0, cudaSetDevice(h0->device));
+  if (stats) memset(stats, 0, sizeof *stats);
+  const int bad = fold_step_records(h0, M, N, nsteps, hc.data(), hcert.data(), stats, EV_LAP, true);
+  if (stats) {
+    auto el = [&](int a, int b) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, get_event(h0, a), get_event(h0, b));
+      return (double)ms;
+    };
+    stats->ms_corr = el(0, 3);  // H2D + K1 + K2 + shard transfer, all devices (overlapped)
+    stats->ms_lap = el(3, 4);
+    stats->ms_d2h = el(4, 5);
+    stats->ms_total = el(0, 5);
+    stats->n_steps = nsteps;
+    int64_t launches = h0->launches - launches0;
+    stats->kernel_launches = launches;
+  }
+  if (flag) return mcd_fail(h0, MCD_ERR_NONFINITE, "NaN or Inf in the expression / copy-number matrix");
+  if ((st = step_status(h0, bad))) return st;
+  h0->last_M = M;
+  h0->last_N = N;
+  h0->last_ldc = ldc;
+  h0->last_assign = out.assign;
   return MCD_OK;
 }
 

@@ -8,6 +8,9 @@
 
 #include "../../include/macrodna_b200.h"
 
+struct mcd_stager;  // stage.cu: host threads + pinned buffers for pageable inputs
+void mcd_stager_destroy(mcd_stager* s);
+
 struct mcd_buffer {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -55,8 +58,9 @@ struct mcd_context {
   mcd_buffer ws[24];
   // pinned host staging
   void* h_stage[2] = {nullptr, nullptr};
-  size_t h_stage_bytes = 0;
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  int stage_next = 0;
+  mcd_stager* stager = nullptr;
   std::vector<cudaEvent_t> ev;
   // shape of the last mcd_cell2cell call whose correlation matrix / assignment are still resident
   int64_t last_M = 0, last_N = 0, last_ldc = 0;
@@ -92,6 +96,12 @@ enum {
 };
 
 int mcd_fail(mcd_context* h, int status, const char* what, cudaError_t e = cudaSuccess);
+// true if p is ordinary (unregistered) host memory
+bool mcd_is_pageable(const void* p);
+// host -> device copy of a [rows, width] float64 block (host pitch src_ld, device pitch dst_ld, elements) from
+// PAGEABLE memory through the handle's pinned staging buffers, asynchronous on `stream` after each block's host copy
+int mcd_staged_h2d(mcd_context* h, double* dst, int64_t dst_ld, const double* src, int64_t src_ld, int64_t width,
+                   int64_t rows, cudaStream_t stream);
 int mcd_ws(mcd_context* h, int slot, size_t bytes, void** out);
 
 #define MCD_CUDA(h, call)                                      \
