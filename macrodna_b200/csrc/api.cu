@@ -2,9 +2,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstddef>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "mcd_internal.cuh"
 
@@ -1223,7 +1226,9 @@ int mcd_cell2cell_multi(mcd_handle* hs, int ndev, const double* rna, int64_t ld_
   if ((st = mcd_ws(h0, WS_MISC, step_out_bytes(M, nsteps), &misc))) return st;
   const StepOut out = carve_step_out(misc, M, nsteps);
   const size_t EV_LAP = 8;
-  if ((st = enqueue_step_loop(h0, C, ldc, Ct, ldct, M, N, out, EV_LAP, false))) return st;
+  // check_finite: the non-finite flag K1 raises lives on the device that saw the bad value; the first solve
+  // re-scans the assembled matrix so that hs[0]'s solver kernels no-op on NaN / Inf instead of iterating on them
+  if ((st = enqueue_step_loop(h0, C, ldc, Ct, ldct, M, N, out, EV_LAP, true))) return st;
   MCD_CUDA(h0, cudaEventRecord(get_event(h0, 4), h0->stream));
   MCD_CUDA(h0, cudaMemcpyAsync(assign, out.assign, (size_t)M * 4, cudaMemcpyDeviceToHost, h0->stream));
   MCD_CUDA(h0, cudaMemcpyAsync(step, out.step, (size_t)M * 4, cudaMemcpyDeviceToHost, h0->stream));
@@ -1487,6 +1492,7 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
   std::vector<mcd_lap_cert> hcert((size_t)(nsteps * batch));
   if (stats) memset(stats, 0, sizeof *stats);
   int bad = 0;
+  double host_enqueue_ms = 0.0;  // wall time of the enqueuing phase of every batch: reported as ms_h2d
   for (int64_t r0 = 0; r0 < nrep; r0 += batch) {
     const int64_t nb = nrep - r0 < batch ? nrep - r0 : batch;
     MCD_CUDA(h, cudaMemcpyAsync(d_cols, dna_cols + r0 * n_sub, (size_t)nb * n_sub * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1497,22 +1503,66 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
     MCD_CUDA(h, cudaMemcpyAsync(d_clss, clss.data(), (size_t)nb * n_sub * 4, cudaMemcpyHostToDevice, h->stream));
     MCD_CUDA(h, cudaEventRecord(get_event(h, 5), h->stream));
     for (int k = 0; k < K; ++k) MCD_CUDA(h, cudaStreamWaitEvent(ws[k]->stream, get_event(h, 5), 0));
-    for (int64_t b = 0; b < nb; ++b) {
-      mcd_context* w = ws[(size_t)(b % K)];
-      void *pc = nullptr, *pct = nullptr;
-      if ((st = mcd_ws(w, WS_SUB_C, (size_t)m_sub * lds * 8, &pc)) || (st = mcd_ws(w, WS_SUB_CT, (size_t)n_sub * ldst * 8, &pct)))
-        return mcd_fail(h, st, "worker workspace");
-      double* subC = static_cast<double*>(pc);
-      double* subCt = static_cast<double*>(pct);
-      dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), grid_rows(m_sub));
-      gather_sub_kernel<<<grid, 256, 0, w->stream>>>(C, h->last_ldc, d_rows, d_cols + b * n_sub, m_sub, n_sub, subC, lds);
-      MCD_LAUNCH_CHECK(w, "gather_sub_kernel");
-      if ((st = mcd_transpose_f64(w, subC, m_sub, n_sub, lds, subCt, ldst))) return mcd_fail(h, st, w->err.c_str());
-      const StepOut out = carve_step_out(static_cast<char*>(p_out) + (size_t)b * rep_bytes, m_sub, nsteps);
-      if ((st = enqueue_step_loop(w, subC, lds, subCt, ldst, m_sub, n_sub, out, 0, false, false,
-                                  n_extra[(size_t)b] > 0 ? d_clss + b * n_sub : nullptr)))
-        return mcd_fail(h, st, w->err.c_str());
+    // Replicates differ a lot in cost (a resampled replicate with a starved clone needs 10x the rounds of a balanced
+    // one), so they are dealt dynamically from a shared counter.  Every worker has its own HOST thread: a cooperative /
+    // cluster launch may block its caller until the stream's earlier work has drained (measured: with one enqueuing
+    // thread 75 % of the sweep's wall time was spent inside launch calls and the workers starved), and the runtime is
+    // thread-safe.  A thread keeps at most two replicates queued on its stream.
+    const auto host_t0 = std::chrono::steady_clock::now();
+    std::atomic<int64_t> next_rep(0);
+    std::vector<int> wstatus((size_t)K, 0);
+    auto worker_main = [&](int k) {
+      mcd_context* w = ws[(size_t)k];
+      if (cudaSetDevice(h->device) != cudaSuccess) {
+        wstatus[(size_t)k] = MCD_ERR_CUDA;
+        return;
+      }
+      int issued = 0;
+      for (;;) {
+        const int64_t b = next_rep.fetch_add(1);
+        if (b >= nb) break;
+        if (issued >= 2) cudaEventSynchronize(get_event(w, 1 + (size_t)(issued & 1)));  // replicate issued - 2 is done
+        int stw;
+        void *pc = nullptr, *pct = nullptr;
+        if ((stw = mcd_ws(w, WS_SUB_C, (size_t)m_sub * lds * 8, &pc)) ||
+            (stw = mcd_ws(w, WS_SUB_CT, (size_t)n_sub * ldst * 8, &pct))) {
+          wstatus[(size_t)k] = stw;
+          return;
+        }
+        double* subC = static_cast<double*>(pc);
+        double* subCt = static_cast<double*>(pct);
+        dim3 grid((unsigned)((n_sub + 1023) / 1024 < 64 ? (n_sub + 1023) / 1024 : 64), grid_rows(m_sub));
+        gather_sub_kernel<<<grid, 256, 0, w->stream>>>(C, h->last_ldc, d_rows, d_cols + b * n_sub, m_sub, n_sub, subC, lds);
+        w->launches++;
+        if (cudaGetLastError() != cudaSuccess) {
+          wstatus[(size_t)k] = mcd_fail(w, MCD_ERR_CUDA, "gather_sub_kernel");
+          return;
+        }
+        const StepOut out = carve_step_out(static_cast<char*>(p_out) + (size_t)b * rep_bytes, m_sub, nsteps);
+        if ((stw = mcd_transpose_f64(w, subC, m_sub, n_sub, lds, subCt, ldst)) ||
+            (stw = enqueue_step_loop(w, subC, lds, subCt, ldst, m_sub, n_sub, out, 0, false, false,
+                                     n_extra[(size_t)b] > 0 ? d_clss + b * n_sub : nullptr))) {
+          wstatus[(size_t)k] = stw;
+          return;
+        }
+        cudaEventRecord(get_event(w, 1 + (size_t)(issued & 1)), w->stream);
+        issued++;
+      }
+    };
+    for (int k = 0; k < K; ++k) {  // events are created on the calling thread (get_event grows a vector)
+      get_event(ws[(size_t)k], 0);
+      get_event(ws[(size_t)k], 1);
+      get_event(ws[(size_t)k], 2);
     }
+    {
+      std::vector<std::thread> threads;
+      for (int k = 1; k < K; ++k) threads.emplace_back(worker_main, k);
+      worker_main(0);
+      for (auto& t : threads) t.join();
+    }
+    for (int k = 0; k < K; ++k)
+      if (wstatus[(size_t)k]) return mcd_fail(h, wstatus[(size_t)k], ws[(size_t)k]->err.c_str());
+    host_enqueue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     for (int k = 0; k < K; ++k) {
       MCD_CUDA(h, cudaEventRecord(get_event(ws[k], 0), ws[k]->stream));
       MCD_CUDA(h, cudaStreamWaitEvent(h->stream, get_event(ws[k], 0), 0));
@@ -1560,6 +1610,7 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
     cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
     stats->ms_lap = ms;
     stats->ms_total = ms;
+    stats->ms_h2d = host_enqueue_ms;
     stats->n_steps = nsteps;
     int64_t launches = h->launches - launches0;
     for (int k = 0; k < K; ++k) launches += ws[k]->launches;

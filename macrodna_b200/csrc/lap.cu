@@ -2161,6 +2161,11 @@ __global__ void __launch_bounds__(JV_THREADS) lap_augment_kernel(LapState s) {
       nsc++;
       steps++;
       bytes += (long long)s.m * 8;
+      if (nsc > s.n + 1 || !(b.v < 1.0e299)) {
+        // more scans than persons, or nothing reachable: only possible on corrupt (non-finite) costs
+        if (tid == 0) s.counters->status |= 1;
+        return;
+      }
       if (b.free_) {
         sink = b.j;
       } else {
@@ -2611,7 +2616,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   // person's values, ~90 % of the lists fail (measured), so the scan-every-row cluster kernel stays.
   bool mh_tail = cluster_tail && n < m;
   if (opt.lap_tail_mh >= 0) mh_tail = cluster_tail && opt.lap_tail_mh != 0;
-  if (mh_tail && cs != 8 && cs != 16) cs = 16;
+  if (mh_tail && cs != 4 && cs != 8 && cs != 16) cs = 16;  // list slots per CTA = 128 / cs must be <= 32
   if (mh_tail) {
     mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
     if (cs > 8)
