@@ -178,6 +178,7 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("ozaki.align", ozaki_align),
     MCD_OPT_I("ozaki.plan", ozaki_plan),
     MCD_OPT_I("k1.generic", k1_generic),
+    MCD_OPT_I("k1.no_stream", k1_no_stream),
     MCD_OPT_D("lap.theta", lap_theta),
     MCD_OPT_D("lap.eps_min", lap_eps_min),
     MCD_OPT_I("lap.scaling", lap_scaling),

@@ -26,6 +26,7 @@ struct mcd_options {
   int ozaki_align = 1;        // "ozaki.align": wave alignment of the K2c producers
   int ozaki_plan = 1;         // "ozaki.plan": unit order of a K2c pass
   int k1_generic = 0;         // "k1.generic": force the generic digit kernel
+  int k1_no_stream = 0;       // "k1.no_stream": one-row-per-CTA digit kernel instead of the persistent streaming one
   double lap_theta = 3.0;     // "lap.theta": eps-scaling factor of the square phases
   double lap_eps_min = 1e-7;  // "lap.eps_min": smallest relative eps of the scaling phases
   int lap_scaling = 1;        // "lap.scaling": eps-scaling phases for n == m

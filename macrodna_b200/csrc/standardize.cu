@@ -288,47 +288,13 @@ __device__ __forceinline__ void ozaki_store_slices(const uint32_t (&lo)[4], cons
 
 // T threads per row, NV4 sweeps of 4 genes per thread (row capacity 4*T*NV4 >= ldk8), digit output only.
 // vec: X is 32-byte aligned and ldx a multiple of 4 (256-bit loads legal).
+// Everything of the digit pass behind the load: v holds the row slice of this thread (4 consecutive genes per k),
+// sum its partial sum.  Shared by the one-row-per-launch-CTA kernel and the persistent streaming kernel below.
 template <int T, int NV4, int NSL>
-__global__ void __launch_bounds__(512, 1)
-standardize_digits(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int G, int64_t ldx,
-                   int vec, double* __restrict__ norms, int* __restrict__ flags, const mcd_ozaki_out oz) {
+__device__ __forceinline__ void digits_row_finish(double (&v)[NV4][4], double sum, int t, int64_t row, bool live, int G,
+                                                  double* __restrict__ norms, int* __restrict__ flags,
+                                                  const mcd_ozaki_out& oz, double* red) {
   constexpr int BLOCK = 512;
-  constexpr int ROWS = BLOCK / T;
-  __shared__ double red[BLOCK / 32];
-  const int t = threadIdx.x % T;
-  const int64_t row = (int64_t)blockIdx.x * ROWS + threadIdx.x / T;
-  const bool live = row < ncells;
-  const double* x = X + (live ? row : 0) * ldx;
-
-  double v[NV4][4];
-  double sum = 0.0;
-#pragma unroll
-  for (int k = 0; k < NV4; ++k) {
-    const int e = 4 * (t + k * T);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (live && e < G) {
-      if (gidx != nullptr) {
-        a0 = __ldg(x + __ldg(gidx + e));
-        if (e + 1 < G) a1 = __ldg(x + __ldg(gidx + e + 1));
-        if (e + 2 < G) a2 = __ldg(x + __ldg(gidx + e + 2));
-        if (e + 3 < G) a3 = __ldg(x + __ldg(gidx + e + 3));
-      } else if (vec && e + 3 < G) {
-        asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
-                     : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
-                     : "l"(x + e));
-      } else {
-        a0 = __ldcs(x + e);
-        if (e + 1 < G) a1 = __ldcs(x + e + 1);
-        if (e + 2 < G) a2 = __ldcs(x + e + 2);
-        if (e + 3 < G) a3 = __ldcs(x + e + 3);
-      }
-    }
-    v[k][0] = a0;
-    v[k][1] = a1;
-    v[k][2] = a2;
-    v[k][3] = a3;
-    sum += (a0 + a1) + (a2 + a3);
-  }
   sum = group_sum<T, BLOCK>(sum, red);
   const double mean = sum / (double)G;
 
@@ -387,12 +353,152 @@ standardize_digits(const double* __restrict__ X, const int* __restrict__ gidx, i
   }
 }
 
+
+template <int T, int NV4, int NSL>
+__global__ void __launch_bounds__(512, 1)
+standardize_digits(const double* __restrict__ X, const int* __restrict__ gidx, int64_t ncells, int G, int64_t ldx,
+                   int vec, double* __restrict__ norms, int* __restrict__ flags, const mcd_ozaki_out oz) {
+  constexpr int BLOCK = 512;
+  constexpr int ROWS = BLOCK / T;
+  __shared__ double red[BLOCK / 32];
+  const int t = threadIdx.x % T;
+  const int64_t row = (int64_t)blockIdx.x * ROWS + threadIdx.x / T;
+  const bool live = row < ncells;
+  const double* x = X + (live ? row : 0) * ldx;
+
+  double v[NV4][4];
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int e = 4 * (t + k * T);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (live && e < G) {
+      if (gidx != nullptr) {
+        a0 = __ldg(x + __ldg(gidx + e));
+        if (e + 1 < G) a1 = __ldg(x + __ldg(gidx + e + 1));
+        if (e + 2 < G) a2 = __ldg(x + __ldg(gidx + e + 2));
+        if (e + 3 < G) a3 = __ldg(x + __ldg(gidx + e + 3));
+      } else if (vec && e + 3 < G) {
+        asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+                     : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3)
+                     : "l"(x + e));
+      } else {
+        a0 = __ldcs(x + e);
+        if (e + 1 < G) a1 = __ldcs(x + e + 1);
+        if (e + 2 < G) a2 = __ldcs(x + e + 2);
+        if (e + 3 < G) a3 = __ldcs(x + e + 3);
+      }
+    }
+    v[k][0] = a0;
+    v[k][1] = a1;
+    v[k][2] = a2;
+    v[k][3] = a3;
+    sum += (a0 + a1) + (a2 + a3);
+  }
+  digits_row_finish<T, NV4, NSL>(v, sum, t, row, live, G, norms, flags, oz, red);
+}
+
+// Persistent streaming form for long rows (T = 512: one row per CTA at a time).  The one-row-per-CTA kernel above
+// runs load -> reduce -> store strictly one after the other on an SM (one 512-thread CTA of 128 registers is all
+// that fits), so HBM reads pause while a row is being reduced and stored: 73 % of the copy peak at C5.  Here a CTA
+// loops over rows and the NEXT row is already on its way into shared memory -- one 1-D bulk copy (TMA,
+// cp.async.bulk) of the whole row, completion on an mbarrier -- while the current row is reduced, turned into digit
+// slices and stored from registers.  Same thread <-> gene mapping and the same arithmetic as above: bit-identical.
+// Needs X 16-byte aligned, ldx and G even (bulk copies move multiples of 16 bytes) and no gene gather.
+template <int NV4, int NSL>
+__global__ void __launch_bounds__(512, 1)
+standardize_digits_stream(const double* __restrict__ X, int64_t ncells, int G, int64_t ldx, double* __restrict__ norms,
+                          int* __restrict__ flags, const mcd_ozaki_out oz) {
+  constexpr int T = 512;
+  extern __shared__ __align__(128) unsigned char k1_smem[];
+  double* buf = reinterpret_cast<double*>(k1_smem);  // [G] the row in flight
+  __shared__ double red[T / 32];
+  __shared__ __align__(8) unsigned long long bar;
+  const int t = threadIdx.x;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  const uint32_t buf_a = (uint32_t)__cvta_generic_to_shared(buf);
+  const uint32_t bytes = (uint32_t)G * 8u;
+  int64_t row = blockIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (row < ncells) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
+                   "l"(X + row * ldx), "r"(bytes), "r"(bar_a)
+                   : "memory");
+    }
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (; row < ncells; row += gridDim.x) {
+    // wait for the row
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K1_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K1_DONE;\n"
+        "bra K1_WAIT;\n"
+        "K1_DONE:\n"
+        "}\n" ::"r"(bar_a),
+        "r"(phase)
+        : "memory");
+    phase ^= 1u;
+    double v[NV4][4];
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const int e = 4 * (t + k * T);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (e + 3 < G) {
+        const double2 lo = *reinterpret_cast<const double2*>(buf + e);
+        const double2 hi = *reinterpret_cast<const double2*>(buf + e + 2);
+        a0 = lo.x, a1 = lo.y, a2 = hi.x, a3 = hi.y;
+      } else if (e < G) {
+        a0 = buf[e];
+        if (e + 1 < G) a1 = buf[e + 1];
+        if (e + 2 < G) a2 = buf[e + 2];
+      }
+      v[k][0] = a0;
+      v[k][1] = a1;
+      v[k][2] = a2;
+      v[k][3] = a3;
+      sum += (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();  // every thread has its slice: the buffer is free for the next row
+    const int64_t nxt = row + gridDim.x;
+    if (t == 0 && nxt < ncells) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
+                   "l"(X + nxt * ldx), "r"(bytes), "r"(bar_a)
+                   : "memory");
+    }
+    digits_row_finish<T, NV4, NSL>(v, sum, t, row, true, G, norms, flags, oz, red);
+  }
+}
+
 template <int T, int NV4>
 int launch_digits(mcd_context* h, const double* X, const int* gidx, int64_t ncells, int G, int64_t ldx, double* norms,
                   const mcd_ozaki_out& oz) {
   constexpr int ROWS = 512 / T;
   const unsigned grid = (unsigned)((ncells + ROWS - 1) / ROWS);
   const int vec = ((reinterpret_cast<uintptr_t>(X) & 31) == 0) && ((ldx & 3) == 0);
+  if (T == 512 && gidx == nullptr && !h->opt.k1_no_stream && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx & 1) == 0 &&
+      (G & 1) == 0 && ncells >= 2 * (int64_t)h->sm_count) {
+    // long rows, plenty of them: persistent CTAs with the next row prefetched by a bulk copy
+    const size_t smem = ((size_t)G * 8 + 127) / 128 * 128;
+    const unsigned pgrid = (unsigned)h->sm_count;
+    if (oz.nsl == 6) {
+      MCD_CUDA(h, cudaFuncSetAttribute(standardize_digits_stream<NV4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      standardize_digits_stream<NV4, 6><<<pgrid, 512, smem, h->stream>>>(X, ncells, G, ldx, norms, h->d_flags, oz);
+    } else {
+      MCD_CUDA(h, cudaFuncSetAttribute(standardize_digits_stream<NV4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      standardize_digits_stream<NV4, 8><<<pgrid, 512, smem, h->stream>>>(X, ncells, G, ldx, norms, h->d_flags, oz);
+    }
+    MCD_LAUNCH_CHECK(h, "standardize_digits_stream");
+    return MCD_OK;
+  }
   if (oz.nsl == 6)
     standardize_digits<T, NV4, 6><<<grid, 512, 0, h->stream>>>(X, gidx, ncells, G, ldx, vec, norms, h->d_flags, oz);
   else
