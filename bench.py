@@ -54,8 +54,8 @@ def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
     capture of `scripts/profile_pass.py C5` (newest profiles/r01_C5_*_ncu_summary.json).  Valid for the C5 workload."""
     p = next((q for q in (os.path.join(ROOT, "profiles", n) for n in (
-        "r01_C5_v6_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json", "r01_C5_final_ncu_summary.json"))
-        if os.path.exists(q)), "")
+        "r02_C5_ncu_summary.json", "r01_C5_v6_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json",
+        "r01_C5_final_ncu_summary.json")) if os.path.exists(q)), "")
     out = {}
     if not os.path.exists(p):
         return out
@@ -646,15 +646,17 @@ def main():
         }
         if args.workload == "C5":
             tr = load_traffic()
-            k1 = "standardize_digits" if (args.precision == "ozaki" and "standardize_digits" in tr) else "standardize_rows"
+            k1 = next((k for k in ("standardize_digits_stream", "standardize_digits") if args.precision == "ozaki" and k in tr),
+                      "standardize_rows")
             if k1 in tr:  # RNA operand launch (the larger of the two)
                 rooflines["standardize"]["traffic"] = max(tr[k1])
             if corr_kernel in tr:
                 rooflines["corr"]["traffic"] = tr[corr_kernel][0]
             if "lap_auction_kernel" in tr:
                 rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
-                rooflines["lap"]["traffic_note"] = ("the step-1 launch of lap_auction_kernel (wide rounds of the 10k x 50k step); "
-                                                    "ncu returns no DRAM counters for the cluster kernels of the narrow rounds")
+                rooflines["lap"]["traffic_note"] = ("one wide-round launch of lap_auction_kernel (a 10k x 40k step) in the "
+                                                    "committed capture profiles/r02_C5_ncu_summary.json; per-kernel "
+                                                    "DRAM bytes of every solver kernel are listed there")
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_digits / standardize_rows", "corr": corr_kernel,

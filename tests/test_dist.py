@@ -57,3 +57,21 @@ def test_gather_rows_world2_gloo(M):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_replicate_partition_and_accuracy():
+    """Config 4 is 'replicas only': replicate r belongs to rank r mod P, every replicate to exactly one rank; the
+    per-replicate accuracy is the reference's (clonal_proportions_resampling.py:191-201)."""
+    import numpy as np
+
+    from macrodna_b200 import dist as mdist
+
+    for world in (1, 2, 4, 8):
+        owners = [mdist.replicate_owner(r, world) for r in range(1000)]
+        counts = np.bincount(owners, minlength=world)
+        assert counts.sum() == 1000 and counts.max() - counts.min() <= 1
+    rna_clone = np.array([0, 0, 1, 1, 2])
+    dna_clone = np.array([0, 1, 2, 2])
+    cols = np.array([3, 0, 1])            # the replicate holds DNA cells 3, 0, 1 (clones 2, 0, 1)
+    assign = np.array([1, 0, 2, 2, 0])    # positions in cols -> clones 0, 2, 1, 1, 2
+    assert mdist.replicate_accuracy(assign, cols, rna_clone, dna_clone) == 4 / 5
