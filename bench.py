@@ -256,6 +256,40 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# go / no-go of a sharded solver: what one per-round price exchange costs on this box
+# ------------------------------------------------------------------------------------------------
+def lap_exchange_probe(torch, world, device, N, rounds_total, ms_lap):
+    """The north star's option for large instances: shard the assignment solver and exchange column prices every
+    bidding round ("NCCL allreduce-max").  One round of such a solver needs at least ONE collective over the N packed
+    64-bit (bid, bidder) keys.  This measures that collective on the box -- NCCL
+    all_reduce(MAX) of N int64, back to back, device-timed -- and projects: every one of the solve's dependent rounds
+    pays it, while only the row-scan part of a round (not its latency chain) shrinks with the shard."""
+    import torch.distributed as dist
+
+    keys = torch.zeros(N, dtype=torch.int64, device=device)
+    for _ in range(20):
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 300
+    e0.record()
+    for _ in range(iters):
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    t = torch.tensor([us], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us = float(t.item())
+    exch_ms = rounds_total * us * 1e-3
+    return {"collective": "NCCL all_reduce(MAX) of %d int64 keys (%d KB), %d ranks, back to back" % (N, N * 8 // 1024, world),
+            "us_per_exchange": us, "dependent_rounds_per_pass": int(rounds_total),
+            "exchange_ms_per_pass": exch_ms, "replicated_solver_ms": ms_lap,
+            "verdict": ("no-go: the exchanges alone cost %.0f ms per pass, the whole replicated solve %.0f ms"
+                        % (exch_ms, ms_lap)) if exch_ms > 0.5 * ms_lap else "worth building"}
+
+
+# ------------------------------------------------------------------------------------------------
 # parity gates printed with the line (SURVEY.md section 8d)
 # ------------------------------------------------------------------------------------------------
 def parity_block(torch, h, M, N, G, rna, dna, res, block_rows=2000, block_cols=500):
@@ -557,6 +591,10 @@ def main():
     # (the resident correlation matrix is now the one of a single-GPU pass over the same instance, at every N)
     parity = parity_block(torch, h, M, N, G, rna_loc if world == 1 else rna_full, dna, res_dev) if rank == 0 else None
     del rna_full
+    shard_probe = None
+    if world > 1:
+        stp = res_dev["stats"]
+        shard_probe = lap_exchange_probe(torch, world, device, N, stp["lap_rounds"], stp["ms_lap"])
     frames = None
     if world == 1 and not args.no_frames:
         frames = frames_block(torch, rna_host, dna_host, res_dev, args.precision)
@@ -687,6 +725,8 @@ def main():
         line["parity"] = parity
         if multi_gpu_check is not None:
             line["multi_gpu_equals_single_gpu"] = multi_gpu_check
+        if shard_probe is not None:
+            line["sharded_solver_go_no_go"] = shard_probe
         if frames is not None:
             line["e2e_frames"] = frames
         if sweep is not None:

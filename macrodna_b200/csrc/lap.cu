@@ -1909,6 +1909,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
     long long tq[4] = {0, 0, 0, 0};
     int cur = 0, stalled = 0;
     uint32_t rpar = 0;
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
     const uint32_t reply_bytes = ncta * (uint32_t)(kc * sizeof(MhEntry) + 16);
 
     auto finalize = [&](int b, Top2 t) {  // one thread records bidder b's bid in shared memory
@@ -1926,9 +1928,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
         stalled = 1;
         break;
       }
+      // (two CTA barriers per certified round: the failure counter is reset by the resolving warp behind the previous
+      //  round's last barrier, and the barrier behind the failure loop only exists when a list failed)
       const long long c0 = clock64();
-      if (tid == 0) s_cnt[0] = 0;
-      __syncthreads();
       // ---- 1. bids from the candidate lists, one warp per bidder (at most two bidders per warp)
       for (int b = warp; b < nu; b += TAIL_WARPS) {
         const int i = s_list[cur][b];
@@ -1986,19 +1988,21 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
         }
       }
       sweeps += nfail;
-      __syncthreads();
+      if (nfail > 0) __syncthreads();  // (uniform) the bids recorded by the failure loop above
       const long long c2 = clock64();
       // ---- 3. resolution by warp 0 (nu <= 32)
       if (warp == 0) {
         int person_out = -1;
         bool applied = false;
-        if (lane < nu) {
+        // winner per object: the lanes bidding on the same object find each other with one match instruction
+        const bool live = lane < nu;
+        const int j = live ? s_bj[lane] : -1 - lane;  // (idle lanes match nobody)
+        const unsigned long long key = live ? s_key[lane] : 0ull;
+        bool win = live;
+        for (unsigned g = __match_any_sync(0xffffffffu, j) & ~(1u << lane); g != 0u; g &= g - 1u)
+          if (s_key[__ffs(g) - 1] > key) win = false;  // (keys carry the person: never equal)
+        if (live) {
           const int i = s_list[cur][lane];
-          const int j = s_bj[lane];
-          const unsigned long long key = s_key[lane];
-          bool win = true;
-          for (int q = 0; q < nu; ++q)
-            if (s_bj[q] == j && s_key[q] > key) win = false;
           person_out = i;  // re-queue unless the bid is applied
           if (win) {
             const double p_old = s.price[j];
@@ -2026,7 +2030,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
         const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
         const unsigned acc = __ballot_sync(0xffffffffu, applied);
         if (person_out >= 0) s_list[cur ^ 1][__popc(has & ((1u << lane) - 1u))] = person_out;
-        if (lane == 0) s_cnt[1] = __popc(has), s_cnt[2] = __popc(acc);
+        if (lane == 0) s_cnt[1] = __popc(has), s_cnt[2] = __popc(acc), s_cnt[0] = 0;
       }
       __syncthreads();
       const int nu_next = s_cnt[1], accepted = s_cnt[2];
