@@ -181,6 +181,7 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("k1.no_stream", k1_no_stream),
     MCD_OPT_D("lap.theta", lap_theta),
     MCD_OPT_D("lap.eps_min", lap_eps_min),
+    MCD_OPT_D("lap.eps0", lap_eps0),
     MCD_OPT_I("lap.scaling", lap_scaling),
     MCD_OPT_D("lap.max_rounds", lap_max_rounds),
     MCD_OPT_I("lap.blocks_per_sm", lap_blocks_per_sm),

@@ -2556,6 +2556,16 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.flags = h->d_flags;
   double theta = opt.lap_theta;  // swept on 10k x 10k: 2 -> 55k rounds, 3 -> 34k, 4 -> 38k, 8 -> 51k
   if (!(theta > 1.0)) theta = 3.0;
+  double eps0 = opt.lap_eps0;
+  if (eps0 <= 0.0 && opt.lap_theta == 3.0 && n >= 4096) {
+    // Large square steps, knobs untouched: start at range/27 and divide by 6.  Round counts of the eps schedules are
+    // erratic (chains of single bidders whose length depends on where the previous phase left the prices); measured on
+    // the square step of ten instances (round 2, scripts/research/gpu_sched.py): 10k x 10k 149 -> 113 ms and
+    // 165 -> 145 ms (34.3k -> 23.6k, 41.9k -> 36.3k rounds), 1k x 1k 15.0 / 17.2 / 10.3 / 18.3 -> 12.2 / 12.6 / 15.2 /
+    // 8.8 ms, 200 x 200 four instances 4-25 % slower (hence the size threshold).
+    eps0 = 1.0 / 27.0;
+    theta = 6.0;
+  }
   const double eps_min_rel = opt.lap_eps_min > 0.0 ? opt.lap_eps_min : 1e-7;
   const bool square_scaling = (n == m && n > 1) && opt.lap_scaling != 0;
   s.max_rounds = opt.lap_max_rounds >= 1.0 ? (long long)opt.lap_max_rounds : 200000 + 64 * (long long)n;
@@ -2564,7 +2574,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   double factors[MAX_PHASES];
   int nphases = 0;
   if (square_scaling)
-    for (double f = 1.0 / theta; f >= eps_min_rel && nphases < MAX_PHASES - 1; f /= theta) factors[nphases++] = f;
+    for (double f = (eps0 > 0.0 ? eps0 : 1.0 / theta); f >= eps_min_rel && nphases < MAX_PHASES - 1; f /= theta)
+      factors[nphases++] = f;
   factors[nphases++] = 0.0;
 
   // a solve that no-ops (non-finite input flag) must still leave a well-defined "nobody assigned" result behind:

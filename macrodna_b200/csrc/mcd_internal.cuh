@@ -29,6 +29,7 @@ struct mcd_options {
   int k1_no_stream = 0;       // "k1.no_stream": one-row-per-CTA digit kernel instead of the persistent streaming one
   double lap_theta = 3.0;     // "lap.theta": eps-scaling factor of the square phases
   double lap_eps_min = 1e-7;  // "lap.eps_min": smallest relative eps of the scaling phases
+  double lap_eps0 = 0.0;      // "lap.eps0": relative eps of the first scaling phase (0 = 1 / lap.theta)
   int lap_scaling = 1;        // "lap.scaling": eps-scaling phases for n == m
   double lap_max_rounds = 0;  // "lap.max_rounds": 0 = 200000 + 64 n
   int lap_blocks_per_sm = 4;  // "lap.blocks_per_sm": cooperative grid of the wide rounds
