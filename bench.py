@@ -212,6 +212,31 @@ def cpu_baseline(M, N, G, clones, budget_s=20.0):
                 "/".join("%.2f" % p[3] for p in pts), expo)}
 
 
+def literal_reference_record(workload, M, N, G):
+    """R0 of SURVEY.md section 8d: the reference file itself (Python pair loop + per-step model build), which only runs
+    where /root/reference exists -- timed in the build container by scripts/time_literal_reference.py and committed
+    (profiles/r02_R0_literal_reference.json).  Single-threaded by construction, so the figure carries over; for the
+    workloads it cannot finish it is extrapolated linearly in pairs and genes and labelled so."""
+    p = os.path.join(ROOT, "profiles", "r02_R0_literal_reference.json")
+    if not os.path.exists(p):
+        return None
+    rec = json.load(open(p))
+    runs = {r["config"]: r for r in rec["runs"]}
+    out = {"measured_in": "build container (8-core Xeon), python scripts/time_literal_reference.py", "cores": 1,
+           "runs": [{k: r[k] for k in ("config", "shape", "R0_literal_s", "R1_port_s", "R0_equals_R1_assignments",
+                                       "R0_us_per_pair")} for r in rec["runs"]]}
+    if workload in runs:
+        out["value"] = runs[workload]["R0_literal_s"]
+        out["extrapolated"] = False
+    elif "C3" in runs:
+        r = runs["C3"]
+        out["value"] = r["R0_us_per_pair"] * 1e-6 * (G / r["shape"][2]) * float(M) * N
+        out["extrapolated"] = True
+        out["how"] = "C3's %.0f us per pair x (G / %d genes) x M*N pairs" % (r["R0_us_per_pair"], r["shape"][2])
+    out["unit"] = UNIT
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -665,7 +690,7 @@ def main():
         corr_peak = {"fp64": FP64_NOMINAL_TFLOPS, "split": peaks["bf16_tflops"],
                      "ozaki": 2.0 * peaks["bf16_tflops"]}[args.precision]
         corr_peak_source = {"fp64": "nominal B200 FP64 (no measured FP64 peak)", "split": peaks["source"] + " bf16",
-                            "ozaki": "2 x %s bf16 GEMM peak (int8 issues at twice the bf16 rate; MEASURED_PEAKS.json has "
+                            "ozaki": "STAND-IN: 2 x %s bf16 GEMM peak (int8 issues at twice the bf16 rate; MEASURED_PEAKS.json has "
                                      "no int8 entry; nominal dense int8 = %.0f TOP/s)" % (peaks["source"],
                                                                                          INT8_NOMINAL_TOPS)}[args.precision]
         corr_kernel = {"fp64": "corr_fp64_kernel", "split": "corr_split_kernel", "ozaki": "corr_ozaki_kernel"}[args.precision]
@@ -735,6 +760,7 @@ def main():
             line["precision_modes"] = companions
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(M, N, G, clones)
+            line["cpu_baseline"]["literal_reference_R0"] = literal_reference_record(args.workload, M, N, G)
         emit(line)
     if world > 1:
         import torch.distributed as dist

@@ -1725,6 +1725,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
 constexpr int MH_NU = 32;           // bidders per round the master takes (one warp resolves them)
 constexpr int MH_KW = 4;            // candidates every warp hands to its CTA's selection
 constexpr uint32_t MH_CMD_BYTES = 16;
+// A narrow-round phase that is still running after this many rounds with a handful of bidders is a price war over a
+// starved group (e.g. a clone with more DNA than remaining RNA cells): the last few persons would need 10^5 more rounds
+// of ~2 us, while an augmenting path costs one Dijkstra tree each.  The phase is cut and the augmenting-path kernel
+// -- exact from any dual-feasible state -- places them.  (Resampled replicates: 150k-270k-round phases.)
+constexpr long long MH_ROUND_BUDGET = 12288;
+constexpr int MH_BUDGET_NU = 16;
 
 struct __align__(16) MhEntry {  // one list entry travelling from a helper to the master
   double w;                     // cost W[i, j]
@@ -1924,7 +1930,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
     };
 
     while (nu > 0) {
-      if (rounds >= s.max_rounds) {
+      if (rounds >= s.max_rounds || (eps == 0.0 && rounds >= MH_ROUND_BUDGET && nu <= MH_BUDGET_NU)) {
         stalled = 1;
         break;
       }
