@@ -184,6 +184,7 @@ const OptEntry kOptions[] = {
     MCD_OPT_D("lap.eps0", lap_eps0),
     MCD_OPT_I("lap.scaling", lap_scaling),
     MCD_OPT_D("lap.max_rounds", lap_max_rounds),
+    MCD_OPT_D("lap.tail_budget", lap_tail_budget),
     MCD_OPT_I("lap.blocks_per_sm", lap_blocks_per_sm),
     MCD_OPT_I("lap.grid_blocks", lap_grid_blocks),
     MCD_OPT_I("lap.list_max_m", lap_list_max_m),

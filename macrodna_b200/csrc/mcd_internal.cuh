@@ -32,6 +32,7 @@ struct mcd_options {
   double lap_eps0 = 0.0;      // "lap.eps0": relative eps of the first scaling phase (0 = 1 / lap.theta)
   int lap_scaling = 1;        // "lap.scaling": eps-scaling phases for n == m
   double lap_max_rounds = 0;  // "lap.max_rounds": 0 = 200000 + 64 n
+  double lap_tail_budget = 0; // "lap.tail_budget": narrow rounds before a long price war goes to augmenting paths (0 = 4096 + m)
   int lap_blocks_per_sm = 4;  // "lap.blocks_per_sm": cooperative grid of the wide rounds
   int lap_grid_blocks = 0;    // "lap.grid_blocks": cap on that grid (0 = none); concurrent solves use a slice of the chip
   int lap_list_max_m = 0;     // "lap.list_max_m": single-CTA list tail up to this many objects
