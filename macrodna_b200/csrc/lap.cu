@@ -2578,7 +2578,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.max_rounds = opt.lap_max_rounds >= 1.0 ? (long long)opt.lap_max_rounds : 200000 + 64 * (long long)n;
   // measured (round 2): budget 2048 vs none: C3 31.7 -> 19.5 ms, C4 55.0 -> 39.7 ms, replicate sweep 20.4 -> 25.2 /s; at
   // m = 50 000 a Dijkstra step scans a 400 KB row (~20 us) and a budget of 2048 costs 512 vs 334 ms: hence m / 2
-  s.tail_budget = opt.lap_tail_budget >= 1.0 ? (long long)opt.lap_tail_budget : (m / 2 > 2048 ? (long long)m / 2 : 2048);
+  // (budgets 2048 / 1024 / 512 / 256 at 200 x 400: 19.4 / 17.9 / 16.6 / 15.9 ms; at 1000 x 2000: 40.6 / 37.2 / 38.0 / 40.9 ms)
+  s.tail_budget = opt.lap_tail_budget >= 1.0 ? (long long)opt.lap_tail_budget : (m / 2 > 1024 ? (long long)m / 2 : 1024);
 
   // eps phases: range/theta, range/theta^2, ... >= eps_min_rel * range, then the exact eps = 0 phase
   double factors[MAX_PHASES];
