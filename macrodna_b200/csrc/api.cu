@@ -193,6 +193,7 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("lap.tail_cluster", lap_tail_cluster),
     MCD_OPT_I("lap.tail_mh", lap_tail_mh),
     MCD_OPT_I("lap.tail_nu", lap_tail_nu),
+    MCD_OPT_I("lap.mh_nu", lap_mh_nu),
     MCD_OPT_I("lap.aug_nu", lap_aug_nu),
     MCD_OPT_I("lap.aug_nu_square", lap_aug_nu_square),
     MCD_OPT_I("lap.rank_select", lap_rank_select),

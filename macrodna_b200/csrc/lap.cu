@@ -1723,7 +1723,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
 // the same way.  The union of the slice tops IS the person's new list (every unlisted object lies below
 // max_c bound_c, which is all the certificate needs, and the row's true top-2 are always in it).
 // ------------------------------------------------------------------------------------------------
-constexpr int MH_NU = 32;           // bidders per round the master takes (one warp resolves them)
+constexpr int MH_NU = 128;          // bidders per round the master can take (threads 0..MH_NU-1 resolve them)
 constexpr int MH_KW = 4;            // candidates every warp hands to its CTA's selection
 constexpr uint32_t MH_CMD_BYTES = 16;
 // A narrow-round phase that is still running after this many rounds with a handful of bidders is a price war over a
@@ -1762,6 +1762,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
   __shared__ unsigned long long s_key[MH_NU];
   __shared__ int s_fail[MH_NU];
   __shared__ int s_cnt[4];  // [0] failures, [1] next count, [2] accepted
+  __shared__ int s_wcnt[MH_NU / 32], s_wacc[MH_NU / 32];  // per resolving warp: persons for the next round, applied bids
   const uint32_t bar_cmd = smem_addr(&s_bars[0]), bar_reply = smem_addr(&s_bars[1]);
 
   const int o0 = min(s.m, (int)cta * mc), o1 = min(s.m, o0 + mc);
@@ -1997,47 +1998,64 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
       sweeps += nfail;
       if (nfail > 0) __syncthreads();  // (uniform) the bids recorded by the failure loop above
       const long long c2 = clock64();
-      // ---- 3. resolution by warp 0 (nu <= 32)
-      if (warp == 0) {
-        int person_out = -1;
-        bool applied = false;
-        // winner per object: the lanes bidding on the same object find each other with one match instruction
-        const bool live = lane < nu;
-        const int j = live ? s_bj[lane] : -1 - lane;  // (idle lanes match nobody)
-        const unsigned long long key = live ? s_key[lane] : 0ull;
+      // ---- 3. resolution by threads 0..MH_NU-1, one bidder each
+      int person_out = -1;
+      bool applied = false;
+      if (tid < MH_NU) {
+        const bool live = tid < nu;
+        const int j = live ? s_bj[tid] : -1;
+        const unsigned long long key = live ? s_key[tid] : 0ull;
         bool win = live;
-        for (unsigned g = __match_any_sync(0xffffffffu, j) & ~(1u << lane); g != 0u; g &= g - 1u)
-          if (s_key[__ffs(g) - 1] > key) win = false;  // (keys carry the person: never equal)
+        if (nu <= 32) {
+          // (warp 0 only) the lanes bidding on the same object find each other with one match instruction
+          for (unsigned g = __match_any_sync(0xffffffffu, live ? j : -1 - lane) & ~(1u << lane); g != 0u; g &= g - 1u)
+            if (s_key[__ffs(g) - 1] > key) win = false;  // (keys carry the person: never equal)
+        } else if (live) {
+          for (int q = 0; q < nu; ++q)  // broadcast reads
+            if (s_bj[q] == j && s_key[q] > key) win = false;
+        }
         if (live) {
-          const int i = s_list[cur][lane];
+          const int i = s_list[cur][tid];
           person_out = i;  // re-queue unless the bid is applied
           if (win) {
             const double p_old = s.price[j];
-            const double p_new = p_old + s_gam[lane];
+            const double p_new = p_old + s_gam[tid];
             const int prev = s.owner[j];
-            const double defend = class_defends<false>(s, i, prev, s_gam[lane]);
+            const double defend = class_defends<false>(s, i, prev, s_gam[tid]);
             if (defend > 0.0) {  // the owner's class has settled lower: the owner raises the price and keeps the object
               s.price[j] = p_old + defend;
               s.profit[prev] -= defend;
               applied = true;  // (progress; the bidder is re-queued: person_out stays i)
-            } else if (prev < 0 || s_gam[lane] > GAMMA_TIE) {
+            } else if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
               applied = true;
               person_out = prev;  // the evicted owner (or -1) bids next round
               s.owner[j] = i;
               if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
               s.price[j] = p_new;
               s.col4row[i] = j;
-              const double prof = (s_bval[lane] + p_old) - p_new;
+              const double prof = (s_bval[tid] + p_old) - p_new;
               s.profit[i] = prof;
               class_settle(s, i, prof);
               if (prev >= 0) s.col4row[prev] = -1;
             }
           }
         }
+        // ordered compaction of the next bidder list over the resolving warps
         const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
         const unsigned acc = __ballot_sync(0xffffffffu, applied);
-        if (person_out >= 0) s_list[cur ^ 1][__popc(has & ((1u << lane) - 1u))] = person_out;
-        if (lane == 0) s_cnt[1] = __popc(has), s_cnt[2] = __popc(acc), s_cnt[0] = 0;
+        if (lane == 0) s_wcnt[warp] = __popc(has), s_wacc[warp] = __popc(acc);
+      }
+      __syncthreads();
+      if (tid < MH_NU) {
+        int off = 0;
+        for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+        const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+        if (person_out >= 0) s_list[cur ^ 1][off + __popc(has & ((1u << lane) - 1u))] = person_out;
+        if (tid == 0) {
+          int tn = 0, ta = 0;
+          for (int w = 0; w < MH_NU / 32; ++w) tn += s_wcnt[w], ta += s_wacc[w];
+          s_cnt[1] = tn, s_cnt[2] = ta, s_cnt[0] = 0;
+        }
       }
       __syncthreads();
       const int nu_next = s_cnt[1], accepted = s_cnt[2];
@@ -2648,7 +2666,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     if (cs > 8)
       MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_mh_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
-  int tail_nu = list_tail ? TAIL_NU : (cluster_tail ? CL_NU : 0);
+  int tail_nu = list_tail ? TAIL_NU : (cluster_tail ? (mh_tail ? opt.lap_mh_nu : CL_NU) : 0);
+  if (mh_tail && (tail_nu < 1 || tail_nu > MH_NU)) tail_nu = MH_NU;
   if (opt.lap_tail_nu >= 0 && opt.lap_tail_nu < tail_nu) tail_nu = opt.lap_tail_nu;
 
   int aug_nu = opt.lap_aug_nu;

@@ -41,6 +41,7 @@ struct mcd_options {
   int lap_tail_cluster = 0;   // "lap.tail_cluster": 0 = automatic (8, or 16 from 32768 objects)
   int lap_tail_mh = -1;       // "lap.tail_mh": -1 = automatic (n < m)
   int lap_tail_nu = -1;       // "lap.tail_nu": -1 = kernel default
+  int lap_mh_nu = 32;         // "lap.mh_nu": bidder count at which the master/helper kernel takes over from the wide rounds
   int lap_aug_nu = 0;         // "lap.aug_nu"
   int lap_aug_nu_square = -1; // "lap.aug_nu_square": -1 = lap.aug_nu
   int lap_rank_select = 1;    // "lap.rank_select"
