@@ -192,8 +192,13 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("lap.list_min_nu", lap_list_min_nu),
     MCD_OPT_I("lap.tail_cluster", lap_tail_cluster),
     MCD_OPT_I("lap.tail_mh", lap_tail_mh),
+    MCD_OPT_I("lap.tail_sym", lap_tail_sym),
+    MCD_OPT_I("lap.prefetch_rows", lap_prefetch_rows),
     MCD_OPT_I("lap.tail_nu", lap_tail_nu),
     MCD_OPT_I("lap.mh_nu", lap_mh_nu),
+    MCD_OPT_I("lap.scale_cut", lap_scale_cut),
+    MCD_OPT_I("lap.scale_full_phases", lap_scale_full_phases),
+    MCD_OPT_D("lap.scale_tail_rounds", lap_scale_tail_rounds),
     MCD_OPT_I("lap.aug_nu", lap_aug_nu),
     MCD_OPT_I("lap.aug_nu_square", lap_aug_nu_square),
     MCD_OPT_I("lap.rank_select", lap_rank_select),

@@ -152,6 +152,12 @@ struct LapState {
   const int* flags;  // [0] != 0: non-finite data was seen upstream -> every solver kernel is a no-op
   long long max_rounds;
   long long tail_budget;  // narrow rounds after which a phase with <= MH_BUDGET_NU bidders goes to augmenting paths
+  // eps-scaling phases (eps > 0) only produce start prices for the next phase, which restarts with everybody
+  // unassigned: such a phase may end early -- once at most scale_cut_nu persons are still bidding, or after
+  // scale_tail_rounds narrow rounds (the last few persons of a phase are one long dependent eviction chain).
+  int scale_cut_nu;
+  long long scale_tail_rounds;
+  int prefetch_rows;  // symmetric cluster tail: L2 prefetch of the likely next bidder's cost row
   // Classes of similar persons (identical cost rows: copies of one resampled DNA cell).  pcls[i] = class id of
   // person i (persons with equal ids are copies), NULL = every person is its own class; ocls[j] = class of the
   // person that owns object j (-1 = free).  A bidder never bids against its own copies: objects held by its class
@@ -892,7 +898,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
   bool stalled = false;
 
   // the exact (eps = 0) phase may hand its last aug_nu persons straight to the augmenting-path kernel
-  const int stop_nu = (eps == 0.0 && aug_nu > tail_nu) ? aug_nu : tail_nu;
+  const int stop_nu = eps == 0.0 ? (aug_nu > tail_nu ? aug_nu : tail_nu) : max(tail_nu, s.scale_cut_nu);
   for (;;) {
     const long long t0 = clock64();
     // (every list that was stamped "being rebuilt" has been rebuilt by the time the loop is left)
@@ -1176,7 +1182,7 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
       ctrl->finished = (aborted || nu == 0 || to_aug) ? 1 : 0;
     } else {
       // scaling phase: its only product is the price vector; a guard hit just ends it early
-      ctrl->in_tail = (!aborted && nu > 0) ? 1 : 0;
+      ctrl->in_tail = (!aborted && nu > s.scale_cut_nu && s.scale_tail_rounds > 0) ? 1 : 0;
     }
     atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->rounds), (unsigned long long)rounds);
     atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bids), (unsigned long long)bids);
@@ -1498,6 +1504,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
 
   long long tq[4] = {0, 0, 0, 0};
   while (nu > 0) {
+    if (eps > 0.0 && (nu <= s.scale_cut_nu || rounds >= s.scale_tail_rounds)) break;  // (uniform over the cluster)
     const long long c0 = clock64();
     // ---- 1. scan.  G warps share one bidder's slice (G = 16, 8, 4, 2, 1 for nu = 1, 2, <=4, <=8, more), so a
     //         round costs one row-latency plus ONE warp reduction per warp whatever the bidder count.
@@ -1684,6 +1691,284 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_cluster_kernel(LapSt
     nu = hdr.x;
     __syncthreads();
     if (hdr.y == 0 && nu > 0) {  // nobody could raise a price: exact ties -> augmentation kernel
+      stalled = 1;
+      break;
+    }
+  }
+  // no CTA may leave while peers can still address its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (cta == 0) {
+    if (tid < nu) s.un[cur_list][tid] = s_list[tid];
+    if (tid == 0) {
+      ctrl->cnt[cur_list] = nu;
+      ctrl->in_tail = 0;
+      if (eps == 0.0) {
+        ctrl->finished = 1;
+        ctrl->stalled = (stalled && nu > 0) ? 1 : 0;
+      }
+      s.counters->rounds += rounds;
+      s.counters->bids += bids;
+      s.counters->bytes += bids * (long long)s.m * 8;
+      for (int q = 0; q < 4; ++q) s.counters->t_phase[4 + q] += tq[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A, narrow part, SYMMETRIC cluster form (round 2; replaces the kernel above for the square phases).
+//
+// The kernel above runs a round as  scan -> partials to CTA 0 -> CTA 0 resolves (two DSMEM reads of the winner's
+// price / owner) -> 8-byte signal to every CTA -> every CTA pulls the packet over DSMEM  : three dependent DSMEM
+// latencies behind the row scan, and seven CTAs idle while CTA 0 resolves.  Here every CTA sends its partial --
+// extended by the price and owner of its two candidates, which it holds anyway -- to EVERY CTA (st.async into a
+// parity-double-buffered inbox, one mbarrier per parity), and every CTA resolves the round by itself: same inputs,
+// same deterministic arithmetic, same result everywhere, so there is nothing to send back.  One DSMEM latency per
+// round; the next scan starts as soon as the local resolution is done.  CTA 0 alone writes the global state.
+// The resolution is the one of the kernel above instruction for instruction: identical trajectories and results.
+// Barrier arming without a race: a peer may be one resolution ahead and send its next partial before this CTA has
+// finished the current round, so the barrier of round r + 1 is armed at the TOP of round r (no peer can send for
+// r + 1 before it has this CTA's round-r partial) for nu_r slots; the bidder count never grows inside a phase, and
+// the warps of the slots that have gone send filler.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) SymPart {  // 48 bytes: one CTA's best / second-best object for one bidder, with price and owner
+  double v1, v2;
+  double p1, p2;
+  int j1, j2, own1, own2;
+};
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_sym_kernel(LapState s, int mc /* objects per CTA, even */) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished || !ctrl->in_tail || s.flags[0]) return;  // uniform over the cluster
+  extern __shared__ __align__(16) unsigned char tsm[];
+  uint32_t cta, ncta;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(ncta));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  // ---- shared-memory carve-up (identical in every CTA, so mapa addresses line up)
+  SymPart* inbox = reinterpret_cast<SymPart*>(tsm);                                   // [2][CL_NU][CL_MAX_CS]
+  Top2* wpart = reinterpret_cast<Top2*>(inbox + 2 * CL_NU * CL_MAX_CS);               // [CL_NU][TAIL_WARPS]
+  int* s_list = reinterpret_cast<int*>(wpart + CL_NU * TAIL_WARPS);                   // [CL_NU]
+  int* s_tmp = s_list + CL_NU;                                                         // [CL_NU]
+  int* s_bj = s_tmp + CL_NU;                                                           // [CL_NU]
+  int* s_ctl = s_bj + CL_NU;                                                           // [4]: next count, accepted bids
+  unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(s_ctl + 4);      // [CL_NU]
+  unsigned long long* bars = s_bkey + CL_NU;                                           // [2]
+  double* sprice = reinterpret_cast<double*>(bars + 2);                                // [mc]
+  int* sowner = reinterpret_cast<int*>(sprice + mc);                                   // [mc]
+  const uint32_t bar0 = smem_addr(bars);
+
+  const int o0 = min(s.m, (int)cta * mc), o1 = min(s.m, o0 + mc);
+  for (int j = o0 + tid; j < o1; j += TAIL_THREADS) {
+    sprice[j - o0] = s.price[j];
+    sowner[j - o0] = s.owner[j];
+  }
+  const int cur_list = ctrl->cur;
+  int nu = ctrl->cnt[cur_list];
+  if (tid < CL_NU) s_list[tid] = tid < nu ? s.un[cur_list][tid] : -1;
+  const double eps = ctrl->eps;
+  if (tid == 0) {
+    tail_mbar_init(bar0, 1);
+    tail_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tail_mbar_expect(bar0, ncta * (uint32_t)nu * (uint32_t)sizeof(SymPart));  // round 0
+  }
+  // this lane's destination (lanes < ncta): the inbox and the two barriers of CTA `lane`
+  const uint32_t dst_inbox = map_to_cta(smem_addr(inbox), lane < (int)ncta ? lane : 0);
+  const uint32_t dst_bar = map_to_cta(bar0, lane < (int)ncta ? lane : 0);
+  __syncthreads();
+  // all barriers of the cluster are initialised and armed before anybody stores remotely
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  long long rounds = 0, bids = 0;
+  int stalled = 0;
+  int slots = nu;  // slots the current round's barrier was armed for (>= nu)
+  const uint32_t pf_slice = (s.vec && s.prefetch_rows) ? ((uint32_t)(o1 - o0) * 8u) & ~15u : 0u;
+  const uint32_t pf_bytes = (s.vec && s.prefetch_rows) ? (uint32_t)s.m * 8u : 0u;  // rows are 16-byte aligned multiples of 16
+  const int span = o1 - o0;
+  long long tq[4] = {0, 0, 0, 0};
+  while (nu > 0) {
+    if (eps > 0.0 && (nu <= s.scale_cut_nu || rounds >= s.scale_tail_rounds)) break;  // (uniform over the cluster)
+    const long long c0 = clock64();
+    const uint32_t par = (uint32_t)rounds & 1u;
+    // arm the NEXT round's barrier (see the header comment) for this round's bidder count
+    if (tid == 0) tail_mbar_expect(bar0 + 8 * (par ^ 1u), ncta * (uint32_t)nu * (uint32_t)sizeof(SymPart));
+    // ---- 1. scan: as in lap_tail_cluster_kernel
+    int G = TAIL_WARPS;
+    while (G > 1 && G * nu > TAIL_WARPS) G >>= 1;
+    const int per_pass = TAIL_WARPS / G;
+    const int sub = (((span + G - 1) / G) + 1) & ~1;  // even sub-slice length
+    const int g = warp % G;
+    const int ws = min(o1, o0 + g * sub), we = min(o1, ws + sub);
+    for (int b = warp / G; b < nu; b += per_pass) {
+      const double* wrow = s.W + (int64_t)s_list[b] * s.ldw;
+      Top2 t{NEG_INF, NEG_INF, -1, -1};
+      if (s.vec) {
+        auto batch = [&](auto depth_tag) {
+          constexpr int D = decltype(depth_tag)::value;
+          for (int j = ws + 2 * lane; j < we; j += D * 64) {
+            double2 wv[D];
+#pragma unroll
+            for (int u = 0; u < D; ++u) {
+              const int jj = j + u * 64;
+              wv[u] = make_double2(NEG_INF, NEG_INF);
+              if (jj + 1 < we)
+                wv[u] = __ldg(reinterpret_cast<const double2*>(wrow + jj));
+              else if (jj < we)
+                wv[u].x = __ldg(wrow + jj);
+            }
+#pragma unroll
+            for (int u = 0; u < D; ++u) {
+              const int jj = j + u * 64;
+              if (jj + 1 < we) {
+                const double2 pv = *reinterpret_cast<const double2*>(sprice + (jj - o0));
+                top2_push_seq(t, wv[u].x - pv.x, jj);
+                top2_push_seq(t, wv[u].y - pv.y, jj + 1);
+              } else if (jj < we) {
+                top2_push_seq(t, wv[u].x - sprice[jj - o0], jj);
+              }
+            }
+          }
+        };
+        if (we - ws <= 128)
+          batch(std::integral_constant<int, 2>{});
+        else
+          batch(std::integral_constant<int, 8>{});
+      } else {
+        for (int j = ws + lane; j < we; j += 32) top2_push_seq(t, __ldg(wrow + j) - sprice[j - o0], j);
+      }
+      t = top2_warp_reduce(t);
+      if (lane == 0) wpart[b * TAIL_WARPS + g] = t;
+    }
+    __syncthreads();
+    const long long c1 = clock64();
+    // ---- 2. warp b merges the G warp partials of bidder b; lane c ships the CTA partial to CTA c.  Slots
+    //         nu .. slots-1 (bidders that have gone since the barrier was armed) get filler.
+    for (int b = warp; b < slots; b += TAIL_WARPS) {
+      Top2 a{NEG_INF, NEG_INF, -1, -1};
+      if (b < nu) {
+        if (lane < G) a = wpart[b * TAIL_WARPS + lane];
+        a = top2_warp_reduce(a);
+      }
+      if (lane < (int)ncta) {
+        double p1 = 0.0, p2 = 0.0;
+        int own1 = -1, own2 = -1;
+        if (a.j1 >= 0) p1 = sprice[a.j1 - o0], own1 = sowner[a.j1 - o0];
+        if (a.j2 >= 0) p2 = sprice[a.j2 - o0], own2 = sowner[a.j2 - o0];
+        // If this CTA's candidate wins, its owner is evicted and bids next round: pull that person's cost row into
+        // L2 now, one exchange + one resolution ahead of the scan that needs it (a cold row is a TLB miss + a DRAM
+        // page miss: ~2 us per scan measured, against ~0.7 us for the exchange and ~0.9 us for the resolution).
+        // Every CTA does this for its own candidate: ncta rows per bidder, one of them the right one.
+        if (lane == 0 && pf_bytes != 0u && own1 >= 0 && nu <= 4)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s.W + (int64_t)own1 * s.ldw), "r"(pf_bytes)
+                       : "memory");
+        const uint32_t dst = dst_inbox + (uint32_t)(((par * CL_NU + b) * CL_MAX_CS + cta) * sizeof(SymPart));
+        const uint32_t rbar = dst_bar + 8 * par;
+        st_async_v2(dst, __double_as_longlong(a.v1), __double_as_longlong(a.v2), rbar);
+        st_async_v2(dst + 16, __double_as_longlong(p1), __double_as_longlong(p2), rbar);
+        st_async_v2(dst + 32, ((uint64_t)(uint32_t)a.j2 << 32) | (uint32_t)a.j1,
+                    ((uint64_t)(uint32_t)own2 << 32) | (uint32_t)own1, rbar);
+      }
+    }
+    // ---- 3. warp 0 of EVERY CTA: merge over the CTAs, resolve, apply to the own slice
+    if (warp == 0) {
+      tail_mbar_wait(bar0 + 8 * par, (uint32_t)(rounds >> 1) & 1u);
+      const long long c2 = clock64();
+      tq[1] += c2 - c1;
+      const SymPart* in = inbox + (size_t)par * CL_NU * CL_MAX_CS;
+      const bool live = lane < nu;
+      Top2 a{NEG_INF, NEG_INF, -1, -1};
+      if (nu <= 4) {  // few bidders (the usual case): one redux reduction per bidder over the CTAs' partials
+        for (int bb = 0; bb < nu; ++bb) {
+          Top2 q{NEG_INF, NEG_INF, -1, -1};
+          if (lane < (int)ncta) {
+            const SymPart& pq = in[bb * CL_MAX_CS + lane];
+            q = Top2{pq.v1, pq.v2, pq.j1, pq.j2};
+          }
+          q = top2_warp_reduce(q);
+          if (lane == bb) a = q;
+        }
+      } else if (live) {
+        for (uint32_t c = 0; c < ncta; ++c) {
+          const SymPart& q = in[lane * CL_MAX_CS + c];
+          top2_merge(a, Top2{q.v1, q.v2, q.j1, q.j2});
+        }
+      }
+      // price / owner of the two candidates travelled with the partial of the CTA that owns them
+      double p1 = 0.0, p2 = 0.0;
+      int own1 = -1, own2 = -1;
+      if (live && a.j1 >= 0) {
+        const SymPart& q = in[lane * CL_MAX_CS + a.j1 / mc];
+        const bool first = q.j1 == a.j1;
+        p1 = first ? q.p1 : q.p2;
+        own1 = first ? q.own1 : q.own2;
+      }
+      if (live && a.j2 >= 0 && eps == 0.0 && a.v1 == a.v2) {
+        const SymPart& q = in[lane * CL_MAX_CS + a.j2 / mc];
+        const bool first = q.j1 == a.j2;
+        p2 = first ? q.p1 : q.p2;
+        own2 = first ? q.own1 : q.own2;
+      }
+      const int i = live ? s_list[lane] : -1;
+      int j = a.j1;
+      double p_old = p1, bval = a.v1;
+      int prev = own1;
+      if (live && eps == 0.0 && a.j2 >= 0 && a.v1 == a.v2 && own1 >= 0 && own2 < 0) {  // exact tie: take the free one
+        j = a.j2, p_old = p2, bval = a.v2, prev = own2;
+      }
+      const double gamma = (a.j2 >= 0 ? (a.v1 - a.v2) : 0.0) + eps;
+      const unsigned long long key = live ? pack_bid(gamma, i) : 0ull;
+      s_bj[lane] = j;
+      s_bkey[lane] = key;
+      __syncwarp();
+      bool win = live;
+      // (a __match_any_sync here instead of the loop was measured slower: 54.0 vs 45.0 Mcycles over the C5 square step)
+      for (int q = 0; q < nu; ++q)
+        if (s_bj[q] == j && s_bkey[q] > key) win = false;
+      const double p_new = p_old + gamma;
+      const bool applied = win && (prev < 0 || gamma > GAMMA_TIE);
+      const bool has = live && (applied ? prev >= 0 : true);
+      const int person_out = applied ? prev : i;
+      const unsigned hmask = __ballot_sync(0xffffffffu, has);
+      const int nu_next = __popc(hmask);
+      const int nacc = __popc(__ballot_sync(0xffffffffu, applied));
+      if (has) s_tmp[__popc(hmask & ((1u << lane) - 1u))] = person_out;
+      __syncwarp();
+      s_list[lane] = lane < nu_next ? s_tmp[lane] : -1;
+      // several bidders next round: their rows' slices are swept in up to six dependent batches per warp -- pull this
+      // CTA's slice of each row into L2 now (one next bidder: its row was requested a round ago, see above)
+      if (pf_slice != 0u && nu_next > 1 && lane < nu_next)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s.W + (int64_t)s_tmp[lane] * s.ldw + o0),
+                     "r"(pf_slice)
+                     : "memory");
+      if (lane == 0) s_ctl[0] = nu_next, s_ctl[1] = nacc;
+      if (applied) {
+        if (j >= o0 && j < o1) {
+          sprice[j - o0] = p_new;
+          sowner[j - o0] = i;
+        }
+        if (cta == 0) {  // global state, read again only by later kernels
+          s.owner[j] = i;
+          s.price[j] = p_new;
+          s.col4row[i] = j;
+          s.profit[i] = (bval + p_old) - p_new;
+          if (prev >= 0) s.col4row[prev] = -1;
+        }
+      }
+      __syncwarp();  // orders this round's col4row stores before the next round's (different lanes, same warp)
+      tq[2] += clock64() - c2;
+    }
+    tq[0] += c1 - c0;
+    if (nu == 1) tq[3] += c1 - c0;  // (research counter: scan cycles of single-bidder rounds)
+    __syncthreads();
+    rounds++;
+    bids += nu;
+    slots = nu;
+    nu = s_ctl[0];
+    const int nacc = s_ctl[1];
+    if (nacc == 0 && nu > 0) {  // nobody could raise a price: exact ties -> augmentation kernel
       stalled = 1;
       break;
     }
@@ -1936,6 +2221,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
         stalled = 1;
         break;
       }
+      if (eps > 0.0 && (nu <= s.scale_cut_nu || rounds >= s.scale_tail_rounds)) break;
       // (two CTA barriers per certified round: the failure counter is reset by the resolving warp behind the previous
       //  round's last barrier, and the barrier behind the failure loop only exists when a list failed)
       const long long c0 = clock64();
@@ -2597,6 +2883,9 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   // measured (round 2): budget 2048 vs none: C3 31.7 -> 19.5 ms, C4 55.0 -> 39.7 ms, replicate sweep 20.4 -> 25.2 /s; at
   // m = 50 000 a Dijkstra step scans a 400 KB row (~20 us) and a budget of 2048 costs 512 vs 334 ms: hence m / 2
   // (budgets 2048 / 1024 / 512 / 256 at 200 x 400: 19.4 / 17.9 / 16.6 / 15.9 ms; at 1000 x 2000: 40.6 / 37.2 / 38.0 / 40.9 ms)
+  s.prefetch_rows = opt.lap_prefetch_rows;
+  s.scale_cut_nu = opt.lap_scale_cut < 0 ? 0 : opt.lap_scale_cut;
+  s.scale_tail_rounds = opt.lap_scale_tail_rounds >= 0.0 ? (long long)opt.lap_scale_tail_rounds : (1ll << 60);
   s.tail_budget = opt.lap_tail_budget >= 1.0 ? (long long)opt.lap_tail_budget : (m / 2 > 1024 ? (long long)m / 2 : 1024);
 
   // eps phases: range/theta, range/theta^2, ... >= eps_min_rel * range, then the exact eps = 0 phase
@@ -2650,11 +2939,26 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
                 2 * CL_NU * sizeof(int) + 2 * CL_MAX_CS * 4 + CL_NU * 12 + 32 + (size_t)mc * 12 + 64;
     if (tail_smem > 220 * 1024) cluster_tail = false;  // object slice does not fit: the wide kernel runs every round
   }
+  // symmetric form of the scan-every-row cluster tail (every CTA resolves the round itself): default
+  bool sym_tail = cluster_tail && opt.lap_tail_sym != 0 && !(n < m && opt.lap_tail_mh != 0);
+  if (sym_tail && opt.lap_tail_cluster <= 0 && m >= 8192) {
+    // measured (C5 square step, 10k objects): 16 CTAs 118.7 ms, 8 CTAs 124.3 ms, 4 CTAs 146.4 ms; at 1000 objects
+    // 8 CTAs 15.6 ms, 16 CTAs 16.1 ms
+    cs = CL_MAX_CS;
+    mc = (int)((((m + cs - 1) / cs) + 1) & ~1LL);
+  }
+  if (sym_tail) {
+    const size_t sym_smem = sizeof(SymPart) * 2 * CL_NU * CL_MAX_CS + sizeof(Top2) * CL_NU * TAIL_WARPS +
+                            3 * CL_NU * sizeof(int) + 16 + CL_NU * 8 + 16 + (size_t)mc * 12 + 64;
+    if (sym_smem > 220 * 1024)
+      sym_tail = false;
+    else
+      tail_smem = sym_smem;
+  }
   if (cluster_tail) {
-    MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tail_smem));
-    if (cs > 8)
-      MCD_CUDA(h, cudaFuncSetAttribute(lap_tail_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const void* tail_fn = sym_tail ? (const void*)lap_tail_sym_kernel : (const void*)lap_tail_cluster_kernel;
+    MCD_CUDA(h, cudaFuncSetAttribute(tail_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    if (cs > 8) MCD_CUDA(h, cudaFuncSetAttribute(tail_fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   // n < m: master/helper tail (candidate lists certify ~90 % of the bids).  n == m: eps-scaling flattens every
   // person's values, ~90 % of the lists fail (measured), so the scan-every-row cluster kernel stays.
@@ -2672,8 +2976,14 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
 
   int aug_nu = opt.lap_aug_nu;
   if (n == m && opt.lap_aug_nu_square >= 0) aug_nu = opt.lap_aug_nu_square;
+  const int scale_cut_nu = s.scale_cut_nu;
+  const long long scale_tail_rounds = s.scale_tail_rounds;
   for (int ph = 0; ph < nphases; ++ph) {
     double factor = factors[ph];
+    // the last lap.scale_full_phases scaling phases always run to completion: the exact phase needs their prices
+    const bool may_cut = ph < nphases - 1 - opt.lap_scale_full_phases;
+    s.scale_cut_nu = may_cut ? scale_cut_nu : 0;
+    s.scale_tail_rounds = may_cut ? scale_tail_rounds : (1ll << 60);
     int rank_select = opt.lap_rank_select;
     void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select};
     MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
@@ -2697,6 +3007,8 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
       cfg.numAttrs = 1;
       if (mh_tail)
         MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_mh_kernel, s, mc));
+      else if (sym_tail)
+        MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_sym_kernel, s, mc));
       else
         MCD_CUDA(h, cudaLaunchKernelEx(&cfg, lap_tail_cluster_kernel, s, mc));
       h->launches++;

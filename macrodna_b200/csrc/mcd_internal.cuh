@@ -40,8 +40,13 @@ struct mcd_options {
   int lap_list_min_nu = 0;    // "lap.list_min_nu"
   int lap_tail_cluster = 0;   // "lap.tail_cluster": 0 = automatic (8, or 16 from 32768 objects)
   int lap_tail_mh = -1;       // "lap.tail_mh": -1 = automatic (n < m)
+  int lap_tail_sym = 1;       // "lap.tail_sym": symmetric cluster tail (every CTA resolves the round); 0 = CTA-0-resolves form
+  int lap_prefetch_rows = 1;  // "lap.prefetch_rows": symmetric tail prefetches the likely next bidder's row into L2
   int lap_tail_nu = -1;       // "lap.tail_nu": -1 = kernel default
   int lap_mh_nu = 32;         // "lap.mh_nu": bidder count at which the master/helper kernel takes over from the wide rounds
+  int lap_scale_cut = 0;      // "lap.scale_cut": eps-scaling phases end once at most this many persons still bid
+  double lap_scale_tail_rounds = -1;  // "lap.scale_tail_rounds": narrow rounds a scaling phase may run (-1 = no limit)
+  int lap_scale_full_phases = 0;  // "lap.scale_full_phases": the last this-many scaling phases are never cut short
   int lap_aug_nu = 0;         // "lap.aug_nu"
   int lap_aug_nu_square = -1; // "lap.aug_nu_square": -1 = lap.aug_nu
   int lap_rank_select = 1;    // "lap.rank_select"
