@@ -193,6 +193,11 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("lap.tail_cluster", lap_tail_cluster),
     MCD_OPT_I("lap.tail_mh", lap_tail_mh),
     MCD_OPT_I("lap.tail_sym", lap_tail_sym),
+    MCD_OPT_I("lap.async", lap_async),
+    MCD_OPT_I("lap.async_nu", lap_async_nu),
+    MCD_OPT_I("lap.async_threads", lap_async_threads),
+    MCD_OPT_I("lap.async_blocks_per_sm", lap_async_blocks_per_sm),
+    MCD_OPT_I("lap.async_stop", lap_async_stop),
     MCD_OPT_I("lap.prefetch_rows", lap_prefetch_rows),
     MCD_OPT_I("lap.tail_nu", lap_tail_nu),
     MCD_OPT_I("lap.mh_nu", lap_mh_nu),
@@ -594,6 +599,8 @@ int fold_step_records(mcd_context* h, int64_t M, int64_t N, int64_t nsteps, cons
               (long long)s, (long long)(R > N ? N : R), (long long)mm, hc[s].rounds, hc[s].bids, hc[s].bytes / (mm * 8),
               hc[s].aug_rows, hc[s].aug_steps, hcert[s].rel_gap);
       for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].t_phase[q]);
+      fprintf(stderr, " async_us=");
+      for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].a_ts[q] / 1000);
       fprintf(stderr, "\n");
     }
   }

@@ -110,6 +110,13 @@ struct LapCtrl {
   int nfail[2];     // bidders whose candidate list failed this round (double buffered by round parity)
   int nhold[2];     // bidders that sat the round out because their list is being rebuilt (same buffering)
   unsigned int barrier[MAX_PHASES];  // one GridBarrier counter per wide-kernel launch
+  // asynchronous wide kernel: next never-bid person, live count of unassigned persons, stop flag
+  unsigned int aq_head, aq_tail;
+  int a_active, a_stop, a_parked, a_guard;
+  unsigned long long a_bids;
+  unsigned long long a_t0;
+  int a_tie;       // an exact tie was met (two equal best values, or a bid that cannot raise a price)
+  int a_fallback;  // ... so the step is redone by the round-synchronous kernel
 };
 
 struct LapState {
@@ -158,6 +165,7 @@ struct LapState {
   int scale_cut_nu;
   long long scale_tail_rounds;
   int prefetch_rows;  // symmetric cluster tail: L2 prefetch of the likely next bidder's cost row
+  ulonglong2* pw;     // [m] asynchronous wide kernel: {price bits, owner as u32} per object, updated by 128-bit CAS
   // Classes of similar persons (identical cost rows: copies of one resampled DNA cell).  pcls[i] = class id of
   // person i (persons with equal ids are copies), NULL = every person is its own class; ocls[j] = class of the
   // person that owns object j (-1 = free).  A bidder never bids against its own copies: objects held by its class
@@ -842,9 +850,12 @@ __device__ __forceinline__ void wide_finalize_bid(const LapState& s, int k, int 
 
 __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, double eps_factor, int phase_idx,
                                                                   int tail_nu, int use_lists, int list_min_nu,
-                                                                  int aug_nu, int rank_select) {
+                                                                  int aug_nu, int rank_select, int only_fallback) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || s.flags[0]) return;  // uniform: written only at the very end of earlier launches
+  // only_fallback: this launch stands behind the asynchronous kernel and runs only if that one met an exact tie
+  // (which optimum it would pick depends on timing: the step is redone here, reproducibly)
+  if (only_fallback && !ctrl->a_fallback) return;
   const int first_phase = phase_idx == 0;
   GridBarrier grid{&ctrl->barrier[phase_idx], 0u};
   __shared__ double cand_v[LAP_THREADS * CAND_T];
@@ -1191,6 +1202,369 @@ __global__ void __launch_bounds__(LAP_THREADS) lap_auction_kernel(LapState s, do
   // row sweeps are counted per CTA (thread 0 of each)
   if (tid == 0 && sweeps > 0)
     atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bytes), (unsigned long long)sweeps * s.m * 8ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A, wide part, ASYNCHRONOUS form (n < m, eps = 0, candidate lists, no classes).
+//
+// The round-synchronous kernel above spends ~15 us per round on two grid barriers and the slowest list rebuild
+// whatever the bidder count; the wide rounds of a 10k x 50k step are ~1 500 such rounds.  An auction does not need
+// rounds (Bertsekas' asynchronous auction): a bid computed from prices that may already be out of date is still a
+// valid bid as long as (a) the prices it saw were not HIGHER than the true ones -- prices only rise, so every value it
+// computed is an upper bound of the true value -- and (b) it is applied only if it still raises the object's price.
+// Here every CTA is a worker that owns one unassigned person at a time and FOLLOWS THE CHAIN:
+//   take the next person that has never bid (atomic counter) -> warp 0 bids from the candidate list (prices + owners
+//   gathered from `pw`, one 16-byte {price, owner} word per object) -> if the list cannot certify its top-2 the whole
+//   CTA sweeps the row and rebuilds it -> the bid is applied with ONE 128-bit compare-and-swap on pw[j] (expected = the
+//   {price, owner} the bid was computed from; on a mismatch the bid is re-checked against the returned state and
+//   either retried or recomputed) -> the worker carries on with the evicted owner.  The number of unassigned persons
+//   never grows, so nobody is ever queued.
+// Exactness: a person that wins j at level b = W_ij - v2 values j at v2 afterwards, and v2 bounds every other object's
+// current value from above (listed objects: prices read <= current; unlisted: the list bound); prices only rise, an
+// object once owned stays owned, unassigned objects keep price 0: the same invariants as the synchronous kernel, so the
+// master/helper tail, the augmenting-path kernel and the certificate continue from its state unchanged.
+// Reproducibility: a tie-free instance has ONE optimum, whatever the order of the bids.  With exact ties the optimum
+// that comes out would depend on timing, so the first exact tie a worker meets (two equal best values, or a bid that
+// cannot raise a price) stops the kernel and the step is redone by the synchronous kernel, whose trajectory is fixed.
+// The kernel stops when at most stop_nu persons are still unassigned (or a bid budget is spent) and leaves
+// price / owner / col4row / profit and the ascending list of unassigned persons behind.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cas128(ulonglong2* addr, unsigned long long& e0, unsigned long long& e1,
+                                       unsigned long long n0, unsigned long long n1) {
+  unsigned long long r0, r1;
+  asm volatile(
+      "{\n"
+      ".reg .b128 cmp, swp, res;\n"
+      "mov.b128 cmp, {%2, %3};\n"
+      "mov.b128 swp, {%4, %5};\n"
+      "atom.relaxed.gpu.global.cas.b128 res, [%6], cmp, swp;\n"
+      "mov.b128 {%0, %1}, res;\n"
+      "}\n"
+      : "=l"(r0), "=l"(r1)
+      : "l"(e0), "l"(e1), "l"(n0), "l"(n1), "l"(addr)
+      : "memory");
+  const bool ok = (r0 == e0) && (r1 == e1);
+  e0 = r0;
+  e1 = r1;
+  return ok;
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Bid of person i from its candidate list against the packed {price, owner} words.  Returns false when the list is
+// missing or cannot certify its top-2.  p1/o1, p2/o2: price and owner of t.j1 / t.j2 as read.
+__device__ __forceinline__ bool list_bid_pw(const LapState& s, int i, int lane, Top2& out, double& p1, int& o1,
+                                            double& p2, int& o2) {
+  const int* lj = s.lj + (int64_t)i * LIST_K;
+  const double* lw = s.lw + (int64_t)i * LIST_K;
+  const int valid = ldm(&s.lvalid[i]);
+  const double b = sortable_f64(ldm(lb_keys(s) + i));
+  int js[LIST_K / 32];
+  double ws[LIST_K / 32];
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q) {
+    js[q] = ldm(lj + lane + 32 * q);
+    ws[q] = ldm(lw + lane + 32 * q);
+  }
+  Top2 t{NEG_INF, NEG_INF, -1, -1};
+  out = t;
+  p1 = p2 = 0.0;
+  o1 = o2 = -1;
+  if (!valid) return false;  // never built: the slots hold garbage
+  double ps[LIST_K / 32];
+  int ow[LIST_K / 32];
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q) {
+    ps[q] = 0.0;
+    ow[q] = -1;
+    if (js[q] >= 0) {
+      const ulonglong2 e = __ldcg(s.pw + js[q]);
+      ps[q] = __longlong_as_double((long long)e.x);
+      ow[q] = (int)(unsigned)e.y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q)
+    if (js[q] >= 0) top2_push(t, ws[q] - ps[q], js[q]);
+  t = top2_warp_reduce(t);
+  out = t;
+  // price / owner of the two winners, from the lanes that hold them
+  double mp1 = 0.0, mp2 = 0.0;
+  int mo1 = -1, mo2 = -1;
+  bool h1 = false, h2 = false;
+#pragma unroll
+  for (int q = 0; q < LIST_K / 32; ++q) {
+    if (js[q] >= 0 && js[q] == t.j1) h1 = true, mp1 = ps[q], mo1 = ow[q];
+    if (js[q] >= 0 && js[q] == t.j2) h2 = true, mp2 = ps[q], mo2 = ow[q];
+  }
+  const unsigned b1 = __ballot_sync(0xffffffffu, h1), b2 = __ballot_sync(0xffffffffu, h2);
+  if (b1 != 0u) {
+    const int src = __ffs(b1) - 1;
+    p1 = __shfl_sync(0xffffffffu, mp1, src);
+    o1 = __shfl_sync(0xffffffffu, mo1, src);
+  }
+  if (b2 != 0u) {
+    const int src = __ffs(b2) - 1;
+    p2 = __shfl_sync(0xffffffffu, mp2, src);
+    o2 = __shfl_sync(0xffffffffu, mo2, src);
+  }
+  return t.j1 >= 0 && t.j2 >= 0 && t.v2 >= b;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, int max_nu, int cont) {
+  LapCtrl* ctrl = s.ctrl;
+  if (ctrl->finished || s.flags[0]) return;  // uniform
+  GridBarrier grid{&ctrl->barrier[MAX_PHASES - 1], 0u};  // (slot 0 belongs to the synchronous kernel's launch)
+  __shared__ double cand_v[NT * CAND_T];
+  __shared__ int cand_j[NT * CAND_T];
+  __shared__ double red[(NT / 32)];
+  __shared__ int s_person, s_res;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int gtid = blockIdx.x * blockDim.x + tid;
+  const int gthreads = gridDim.x * blockDim.x;
+  const unsigned long long FREE = 0xffffffffull;  // owner word of a free object (-1 as u32)
+
+  // cont = 0: the kernel starts the step (everybody unassigned, prices 0).  cont = 1: it takes over from the
+  // round-synchronous kernel, which ran the rounds with thousands of bidders (there the work per round, not the two
+  // barriers, is what a round costs): prices / owners are packed, the persons to place are its bidder list.
+  if (cont && !ctrl->in_tail) return;  // uniform (written at the end of the previous launch)
+  const int* worklist = cont ? s.un[ctrl->cur] : nullptr;
+  const int nwork = cont ? ctrl->cnt[ctrl->cur] : s.n;
+  if (cont) {
+    for (int j = gtid; j < s.m; j += gthreads)
+      s.pw[j] = make_ulonglong2((unsigned long long)__double_as_longlong(s.price[j]), (unsigned long long)(unsigned)s.owner[j]);
+  } else {
+    for (int j = gtid; j < s.m; j += gthreads) {
+      s.pw[j] = make_ulonglong2(0ull, FREE);  // price +0.0, nobody
+      s.price[j] = 0.0;
+      s.owner[j] = -1;
+      s.key[j] = 0ull;
+    }
+    for (int i = gtid; i < s.n; i += gthreads) {
+      s.col4row[i] = -1;
+      s.lvalid[i] = 0;
+      s.done[i] = 0;
+    }
+  }
+  if (gtid == 0) {
+    ctrl->aq_head = 0u;
+    ctrl->a_active = nwork;
+    ctrl->a_stop = nwork <= stop_nu ? 1 : 0;
+    ctrl->a_parked = 0;
+    ctrl->a_bids = 0ull;
+    ctrl->a_guard = 0;
+    ctrl->a_tie = 0;
+    ctrl->a_fallback = 0;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    ctrl->a_t0 = now;
+  }
+  grid.sync();
+  unsigned long long T0 = 0;
+  if (gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(T0));
+
+  // One CTA = one worker.  It takes the next person that has never bid (an atomic counter over 0 .. n-1) and FOLLOWS
+  // THE CHAIN: when its bid evicts an owner, the worker carries on with the evicted person itself -- the number of
+  // unassigned persons never grows, so nobody ever has to be queued, and a hop of a chain costs one list bid + one
+  // compare-and-swap (a hand-over through a queue cost as much again: measured 23-30 ms -> see DESIGN for the C5 step).
+  // Warp 0 bids from the list; a list that cannot certify its top-2 is rebuilt by the whole CTA (a single warp needs
+  // ~200 dependent load batches for a 400 KB row: measured, the kernel was then no faster than the synchronous one).
+  long long bids = 0, scans = 0;
+  const long long max_bids = 1000000ll + 1000ll * s.n;
+  for (;;) {
+    if (tid == 0) {
+      int i = -1;
+      if (ld_relaxed_s32(&ctrl->a_stop) == 0) {
+        const unsigned h = atomicAdd(&ctrl->aq_head, 1u);
+        if (h < (unsigned)nwork) i = cont ? ldm(worklist + h) : (int)h;
+      }
+      s_person = i;
+    }
+    __syncthreads();
+    int i = s_person;
+    if (i < 0) break;
+    // ---- bid until the chain ends on a free object, the person is parked on an exact tie, or the kernel stops.
+    //      Warp 0 runs the hops of the chain by itself; the CTA only meets when a list has to be rebuilt.
+    int fails = 0, last_scanned = -1;
+    for (;;) {
+      if (warp == 0) {
+        int res;  // -1 = chain ended; -3 = rebuild the list of s_person
+        int tie_tries = 0;
+        for (;;) {
+          Top2 t;
+          double p1, p2;
+          int o1, o2;
+          res = -1;  // (>= 0: placed, carry on with this evicted person; -2 = bid again)
+          if (!list_bid_pw(s, i, lane, t, p1, o1, p2, o2)) {
+            res = -3;
+          } else if (lane == 0) {
+            int j = t.j1, own_read = o1;
+            double p_read = p1;
+            if (t.v1 == t.v2 && o1 >= 0 && o2 < 0) {
+              // two equal best values, one of the objects free: which of several optima comes out would depend on
+              // timing from here on.  Stop; the round-synchronous kernel redoes the step reproducibly.
+              atomicExch(&ctrl->a_tie, 1);
+              atomicExch(&ctrl->a_stop, 1);
+              j = t.j2, own_read = o2, p_read = p2;  // exact tie: take the free one
+            }
+            const double level = p_read + (t.v1 - t.v2);  // the price up to which i prefers j to everything else
+            unsigned long long e0 = (unsigned long long)__double_as_longlong(p_read), e1 = (unsigned long long)(unsigned)own_read;
+            bool first = true, parked = false, placed = false;
+            int prev = -1;
+            for (;;) {
+              const double p_cur = __longlong_as_double((long long)e0);
+              const int own_cur = (int)(unsigned)e1;
+              if (own_cur >= 0 && !(level - p_cur > GAMMA_TIE)) {
+                parked = first;  // the state the bid was computed from: an exact tie; a newer state: bid again
+                break;
+              }
+              const double p_new = level > p_cur ? level : p_cur;  // (a free object keeps its price on a tie)
+              if (cas128(s.pw + j, e0, e1, (unsigned long long)__double_as_longlong(p_new), (unsigned long long)(unsigned)i)) {
+                prev = own_cur;
+                placed = true;
+                // the sweeps' copy of the price: prices are >= 0, so their bit patterns order like the values and an
+                // atomic max keeps the copy monotone even when two winners' updates arrive out of order
+                atomicMax(reinterpret_cast<unsigned long long*>(s.price + j), (unsigned long long)__double_as_longlong(p_new));
+                break;
+              }
+              first = false;
+            }
+            bids++;
+            if (placed) {
+              res = prev;  // -1: the chain ended on a free object
+              if (prev < 0) {
+                const int left = atomicSub(&ctrl->a_active, 1) - 1;
+                if (left <= stop_nu) atomicExch(&ctrl->a_stop, 1);
+                if (left == stop_nu || (left >= 64 && left <= 4096 && (left & (left - 1)) == 0)) {
+                  unsigned long long now;
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                  const int slot = left == stop_nu ? 7 : 12 - (31 - __clz(left));  // 4096 -> 0 ... 64 -> 6
+                  s.counters->a_ts[slot] = (long long)(now - ctrl->a_t0);
+                }
+              }
+            } else if (parked && ++tie_tries <= 32) {
+              // the bid cannot raise the price (exact or near tie on an owned object).  Mostly transient: the prices
+              // around it are moving.  Bid again a little later (the synchronous kernel re-queues such a bidder too).
+              res = -2;
+              __nanosleep(400);
+            } else if (parked) {
+              res = -1;  // a standing tie: redo the step reproducibly
+              atomicExch(&ctrl->a_tie, 1);
+              atomicExch(&ctrl->a_stop, 1);
+              atomicAdd(&ctrl->a_parked, 1);
+              atomicSub(&ctrl->a_active, 1);
+            } else {
+              res = -2;
+            }
+            if ((bids & 63) == 0) {
+              const unsigned long long tot = atomicAdd(&ctrl->a_bids, 64ull) + 64ull;
+              if ((long long)tot > max_bids) atomicExch(&ctrl->a_guard, 1), atomicExch(&ctrl->a_stop, 1);
+            }
+            // (a worker in the middle of a chain leaves its person unassigned when the kernel stops: the epilogue finds it)
+            if (res != -1 && ld_relaxed_s32(&ctrl->a_stop) != 0) res = -1;
+          }
+          res = __shfl_sync(0xffffffffu, res, 0);
+          if (res >= 0) i = res, tie_tries = 0;
+          if (res == -1 || res == -3) break;
+        }
+        if (lane == 0) s_res = res, s_person = i;
+      }
+      __syncthreads();
+      const int res = s_res;
+      i = s_person;
+      __syncthreads();  // (s_res / s_person are rewritten by the next attempt)
+      if (res != -3) break;
+      fails = (i == last_scanned) ? fails + 1 : 1;
+      last_scanned = i;
+      if (fails > 8 || ld_relaxed_s32(&ctrl->a_stop) != 0) {
+        // prices of its candidates keep moving under the sweeps (or the kernel has stopped): leave it to the tail
+        if (tid == 0 && fails > 8) {
+          atomicAdd(&ctrl->a_parked, 1);
+          if (atomicSub(&ctrl->a_active, 1) - 1 <= stop_nu) atomicExch(&ctrl->a_stop, 1);
+        }
+        break;
+      }
+      (void)full_scan_build<NT, true>(s, i, cand_v, cand_j, red);
+      __threadfence();  // the list is read by whichever CTA handles this person next
+      scans++;
+    }
+  }
+  unsigned long long T1 = 0, T2 = 0;
+  if (gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(T1));
+  __syncthreads();
+  grid.sync();
+  if (gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(T2));
+  // ---- epilogue: unpack the object state, derive the person state from it
+  if (cont) {
+    for (int i = gtid; i < s.n; i += gthreads) s.col4row[i] = -1;
+    grid.sync();
+  }
+  for (int j = gtid; j < s.m; j += gthreads) {
+    const ulonglong2 e = __ldcg(s.pw + j);
+    const double p = __longlong_as_double((long long)e.x);
+    const int own = (int)(unsigned)e.y;
+    s.price[j] = p;
+    s.owner[j] = own;
+    if (own >= 0) {
+      s.col4row[own] = j;
+      s.profit[own] = __ldg(s.W + (int64_t)own * s.ldw + j) - p;
+    }
+  }
+  if (tid == 0 && (bids | scans) != 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bids), (unsigned long long)bids);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->bytes), (unsigned long long)scans * s.m * 8ull);
+  }
+  grid.sync();
+  if (blockIdx.x == 0) {  // ascending list of the unassigned persons
+    __shared__ int s_wsum[(NT / 32)];
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < s.n; i0 += NT) {
+      const int i = i0 + tid;
+      const bool un = i < s.n && ldm(&s.col4row[i]) < 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, un);
+      if (lane == 0) s_wsum[warp] = __popc(bal);
+      __syncthreads();
+      int off = s_base;
+      for (int wq = 0; wq < warp; ++wq) off += s_wsum[wq];
+      if (un) s.un[0][off + __popc(bal & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int wq = 0; wq < (NT / 32); ++wq) tot += s_wsum[wq];
+        s_base += tot;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int nu = s_base;
+      const bool tie = !cont && ctrl->a_tie != 0 && nu > 0;  // (no fallback behind a hand-over from the synchronous kernel)
+      ctrl->a_fallback = tie ? 1 : 0;
+      const bool aborted = (ctrl->a_guard != 0 || nu > max_nu) && !tie;
+      ctrl->cnt[0] = nu;
+      ctrl->cnt[1] = 0;
+      ctrl->cur = 0;
+      ctrl->eps = 0.0;
+      ctrl->in_tail = (!aborted && !tie && nu > 0) ? 1 : 0;
+      ctrl->stalled = (aborted && nu > 0) ? 1 : 0;
+      ctrl->finished = (aborted || nu == 0) ? 1 : 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters->rounds), 1ull);
+      unsigned long long T3;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(T3));
+      // (ns) bidding until CTA 0 saw the stop flag, drain of the other workers, epilogue; persons parked
+      s.counters->t_phase[0] += (long long)(T1 - T0);
+      s.counters->t_phase[1] += (long long)(T2 - T1);
+      s.counters->t_phase[2] += (long long)(T3 - T2);
+      s.counters->t_phase[3] += ctrl->a_parked;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2583,10 +2957,11 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   ctrl->in_tail = 0;
   ctrl->eps = 0.0;
   ctrl->nfail[0] = ctrl->nfail[1] = 0;
+  ctrl->a_tie = ctrl->a_fallback = 0;
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
-    for (int q = 0; q < 8; ++q) counters->t_phase[q] = 0;
+    for (int q = 0; q < 8; ++q) counters->t_phase[q] = 0, counters->a_ts[q] = 0;
   }
 }
 
@@ -2805,6 +3180,7 @@ size_t mcd_lap_workspace_bytes(int64_t n, int64_t m) {
   b += align_up((n + 1) * 8, 256);      // sc_val
   b += align_up(m * 4, 256);            // ocls
   b += align_up(n * 8, 256);            // clevel
+  b += align_up(m * 16, 256);           // pw
   return b;
 }
 
@@ -2861,6 +3237,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   s.sc_val = reinterpret_cast<double*>(take((n + 1) * 8));
   s.ocls = reinterpret_cast<int*>(take(m * 4));
   s.clevel = reinterpret_cast<unsigned long long*>(take(n * 8));
+  s.pw = reinterpret_cast<ulonglong2*>(take(m * 16));
   s.pcls = (n < m) ? person_class : nullptr;  // classes ride on the candidate-list bids, which only n < m uses
   s.col4row = col4row;
   s.counters = d_counters;
@@ -2976,6 +3353,23 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
 
   int aug_nu = opt.lap_aug_nu;
   if (n == m && opt.lap_aug_nu_square >= 0) aug_nu = opt.lap_aug_nu_square;
+  // asynchronous wide kernel: the exact phase of a rectangular step with candidate lists and the master/helper tail
+  bool use_async = opt.lap_async != 0 && n < m && use_lists != 0 && mh_tail && tail_nu > 0 && s.pcls == nullptr &&
+                   m >= 256 && nphases == 1 && s.list_k == LIST_K;
+  int async_blocks = 0;
+  const int async_threads = opt.lap_async_threads == 128 ? 128 : 256;
+  const void* async_fn = async_threads == 128 ? (const void*)lap_async_kernel<128> : (const void*)lap_async_kernel<256>;
+  if (use_async) {
+    int aper = 0;
+    MCD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aper, async_fn, async_threads, 0));
+    const int awant = opt.lap_async_blocks_per_sm > 0 ? opt.lap_async_blocks_per_sm : 16;
+    if (aper < 1) {
+      use_async = false;
+    } else {
+      async_blocks = h->sm_count * (aper < awant ? aper : awant);
+      if (opt.lap_grid_blocks > 0 && opt.lap_grid_blocks < async_blocks) async_blocks = opt.lap_grid_blocks;
+    }
+  }
   const int scale_cut_nu = s.scale_cut_nu;
   const long long scale_tail_rounds = s.scale_tail_rounds;
   for (int ph = 0; ph < nphases; ++ph) {
@@ -2985,9 +3379,32 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
     s.scale_cut_nu = may_cut ? scale_cut_nu : 0;
     s.scale_tail_rounds = may_cut ? scale_tail_rounds : (1ll << 60);
     int rank_select = opt.lap_rank_select;
-    void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select};
-    MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
-                                            h->stream));
+    if (use_async) {
+      int stop_nu = opt.lap_async_stop > 0 && opt.lap_async_stop < tail_nu ? opt.lap_async_stop : tail_nu;
+      int max_nu = MH_NU, cont = 0;
+      if (opt.lap_async_nu > tail_nu) {  // the rounds with more than lap.async_nu bidders stay round-synchronous
+        int wide_stop = opt.lap_async_nu, no = 0;
+        void* args[] = {&s, &factor, &ph, &wide_stop, &use_lists, &list_min_nu, &aug_nu, &rank_select, &no};
+        MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args,
+                                                0, h->stream));
+        h->launches++;
+        cont = 1;
+      }
+      void* aargs[] = {&s, &stop_nu, &max_nu, &cont};
+      MCD_CUDA(h, cudaLaunchCooperativeKernel(async_fn, dim3(async_blocks), dim3(async_threads), aargs, 0, h->stream));
+      if (cont == 0) {  // exact ties: the step is redone round-synchronously (a no-op launch otherwise)
+        int yes = 1;
+        void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select, &yes};
+        MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args,
+                                                0, h->stream));
+        h->launches++;
+      }
+    } else {
+      int no = 0;
+      void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select, &no};
+      MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args, 0,
+                                              h->stream));
+    }
     h->launches++;
     if (tail_nu > 0 && list_tail) {
       lap_tail_list_kernel<<<1, TAIL_THREADS, 0, h->stream>>>(s);

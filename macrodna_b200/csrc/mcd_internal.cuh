@@ -42,6 +42,11 @@ struct mcd_options {
   int lap_tail_mh = -1;       // "lap.tail_mh": -1 = automatic (n < m)
   int lap_tail_sym = 1;       // "lap.tail_sym": symmetric cluster tail (every CTA resolves the round); 0 = CTA-0-resolves form
   int lap_prefetch_rows = 1;  // "lap.prefetch_rows": symmetric tail prefetches the likely next bidder's row into L2
+  int lap_async = 1;          // "lap.async": asynchronous (round-free) wide kernel for the rectangular steps
+  int lap_async_nu = 0;       // "lap.async_nu": rounds with more bidders than this stay round-synchronous (0 = none)
+  int lap_async_threads = 256;  // "lap.async_threads": threads per worker CTA (128 or 256)
+  int lap_async_blocks_per_sm = 0;  // "lap.async_blocks_per_sm": 0 = as many as fit
+  int lap_async_stop = 8;     // "lap.async_stop": unassigned persons at which the master/helper tail takes over
   int lap_tail_nu = -1;       // "lap.tail_nu": -1 = kernel default
   int lap_mh_nu = 32;         // "lap.mh_nu": bidder count at which the master/helper kernel takes over from the wide rounds
   int lap_scale_cut = 0;      // "lap.scale_cut": eps-scaling phases end once at most this many persons still bid
@@ -168,6 +173,8 @@ struct mcd_lap_counters {  // device-resident, one per solve
   int pad;
   long long t_phase[8];  // SM cycles seen by CTA 0. wide kernel: bidding, barrier 1, resolution, barrier 2;
                          // cluster kernel: scan, wait partials, resolve+send, wait packet
+  long long a_ts[8];     // asynchronous wide kernel (debug): ns from its start until <= 4096, 2048, 1024, 512, 256, 128, 64,
+                         // stop_nu persons were left unassigned
 };
 struct mcd_lap_cert {  // device-resident, one per solve: the dual certificate (lap.cu, lap_cert_* kernels)
   double lambda;         // min price over the assigned objects
