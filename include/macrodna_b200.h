@@ -101,7 +101,9 @@ void* mcd_stream(mcd_handle h);
  * Behaviour / tuning switches of a handle (all have working defaults; nothing on the product path reads the
  * environment).  Names: "certify" (1), "debug" (0: per-step solver counters on stderr), "corr_only" (0; 1 = the
  * fused driver stops after the correlation matrix, which stays resident for the view calls; assign comes back
- * as -1), "ozaki.slices" (0 = auto),
+ * as -1), "deterministic" (0; 1 = round-synchronous solver kernels only: the bid order, and with it the optimum
+ * picked on inputs with exact ties, is then fixed; the default asynchronous kernel of the rectangular steps gives the
+ * same unique optimum on tie-free inputs and redoes a step synchronously when it meets exact ties), "ozaki.slices" (0 = auto),
  * "ozaki.align", "ozaki.plan", "k1.generic", "k1.no_stream", and the solver knobs "lap.theta", "lap.eps_min", "lap.eps0", "lap.scaling",
  * "lap.max_rounds", "lap.tail_budget", "lap.blocks_per_sm", "lap.grid_blocks", "lap.list_max_m", "lap.lists", "lap.list_min_nu",
  * "lap.tail_cluster", "lap.tail_mh", "lap.tail_sym", "lap.async", "lap.async_nu", "lap.async_threads", "lap.async_blocks_per_sm", "lap.async_stop", "lap.prefetch_rows", "lap.tail_nu", "lap.mh_nu", "lap.scale_cut", "lap.scale_tail_rounds", "lap.scale_full_phases", "lap.aug_nu", "lap.aug_nu_square", "lap.rank_select",

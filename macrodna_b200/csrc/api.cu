@@ -174,6 +174,7 @@ const OptEntry kOptions[] = {
     MCD_OPT_I("certify", certify),
     MCD_OPT_I("debug", debug),
     MCD_OPT_I("corr_only", corr_only),
+    MCD_OPT_I("deterministic", deterministic),
     MCD_OPT_I("ozaki.slices", ozaki_slices),
     MCD_OPT_I("ozaki.align", ozaki_align),
     MCD_OPT_I("ozaki.plan", ozaki_plan),

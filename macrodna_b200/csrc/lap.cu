@@ -1254,41 +1254,48 @@ __device__ __forceinline__ int ld_relaxed_s32(const int* p) {
   return v;
 }
 
-// Bid of person i from its candidate list against the packed {price, owner} words.  Returns false when the list is
-// missing or cannot certify its top-2.  p1/o1, p2/o2: price and owner of t.j1 / t.j2 as read.
-__device__ __forceinline__ bool list_bid_pw(const LapState& s, int i, int lane, Top2& out, double& p1, int& o1,
-                                            double& p2, int& o2) {
-  const int* lj = s.lj + (int64_t)i * LIST_K;
-  const double* lw = s.lw + (int64_t)i * LIST_K;
-  const int valid = ldm(&s.lvalid[i]);
-  const double b = sortable_f64(ldm(lb_keys(s) + i));
+// A person's candidate list in registers (lane l holds entries l, l + 32, l + 64, l + 96).
+struct ListRegs {
+  int valid;
+  double bound;
   int js[LIST_K / 32];
   double ws[LIST_K / 32];
+};
+__device__ __forceinline__ void load_list(const LapState& s, int i, int lane, ListRegs& L) {
+  const int* lj = s.lj + (int64_t)i * LIST_K;
+  const double* lw = s.lw + (int64_t)i * LIST_K;
+  L.valid = ldm(&s.lvalid[i]);
+  L.bound = sortable_f64(ldm(lb_keys(s) + i));
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q) {
-    js[q] = ldm(lj + lane + 32 * q);
-    ws[q] = ldm(lw + lane + 32 * q);
+    L.js[q] = ldm(lj + lane + 32 * q);
+    L.ws[q] = ldm(lw + lane + 32 * q);
   }
+}
+// Bid from a list against the packed {price, owner} words.  Returns false when the list is missing or cannot certify
+// its top-2.  p1/o1, p2/o2: price and owner of t.j1 / t.j2 as read.
+__device__ __forceinline__ bool list_bid_pw(const LapState& s, const ListRegs& L, int lane, Top2& out, double& p1, int& o1,
+                                            double& p2, int& o2) {
   Top2 t{NEG_INF, NEG_INF, -1, -1};
   out = t;
   p1 = p2 = 0.0;
   o1 = o2 = -1;
-  if (!valid) return false;  // never built: the slots hold garbage
+  if (!L.valid) return false;  // never built: the slots hold garbage
   double ps[LIST_K / 32];
   int ow[LIST_K / 32];
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q) {
     ps[q] = 0.0;
     ow[q] = -1;
-    if (js[q] >= 0) {
-      const ulonglong2 e = __ldcg(s.pw + js[q]);
+    if (L.js[q] >= 0) {
+      const ulonglong2 e = __ldcg(s.pw + L.js[q]);
       ps[q] = __longlong_as_double((long long)e.x);
       ow[q] = (int)(unsigned)e.y;
     }
   }
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q)
-    if (js[q] >= 0) top2_push(t, ws[q] - ps[q], js[q]);
+    if (L.js[q] >= 0) top2_push(t, L.ws[q] - ps[q], L.js[q]);
   t = top2_warp_reduce(t);
   out = t;
   // price / owner of the two winners, from the lanes that hold them
@@ -1297,8 +1304,8 @@ __device__ __forceinline__ bool list_bid_pw(const LapState& s, int i, int lane, 
   bool h1 = false, h2 = false;
 #pragma unroll
   for (int q = 0; q < LIST_K / 32; ++q) {
-    if (js[q] >= 0 && js[q] == t.j1) h1 = true, mp1 = ps[q], mo1 = ow[q];
-    if (js[q] >= 0 && js[q] == t.j2) h2 = true, mp2 = ps[q], mo2 = ow[q];
+    if (L.js[q] >= 0 && L.js[q] == t.j1) h1 = true, mp1 = ps[q], mo1 = ow[q];
+    if (L.js[q] >= 0 && L.js[q] == t.j2) h2 = true, mp2 = ps[q], mo2 = ow[q];
   }
   const unsigned b1 = __ballot_sync(0xffffffffu, h1), b2 = __ballot_sync(0xffffffffu, h2);
   if (b1 != 0u) {
@@ -1311,7 +1318,7 @@ __device__ __forceinline__ bool list_bid_pw(const LapState& s, int i, int lane, 
     p2 = __shfl_sync(0xffffffffu, mp2, src);
     o2 = __shfl_sync(0xffffffffu, mo2, src);
   }
-  return t.j1 >= 0 && t.j2 >= 0 && t.v2 >= b;
+  return t.j1 >= 0 && t.j2 >= 0 && t.v2 >= L.bound;
 }
 
 template <int NT>
@@ -1396,12 +1403,22 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
       if (warp == 0) {
         int res;  // -1 = chain ended; -3 = rebuild the list of s_person
         int tie_tries = 0;
+        ListRegs L, N;
+        bool have = false;  // L already holds person i's list (fetched speculatively, see below)
         for (;;) {
           Top2 t;
           double p1, p2;
           int o1, o2;
           res = -1;  // (>= 0: placed, carry on with this evicted person; -2 = bid again)
-          if (!list_bid_pw(s, i, lane, t, p1, o1, p2, o2)) {
+          if (!have) load_list(s, i, lane, L);
+          have = false;
+          const bool ok = list_bid_pw(s, L, lane, t, p1, o1, p2, o2);
+          // The person this bid will evict, if it is applied, is the owner just read: request ITS list now, so that
+          // the loads travel while the compare-and-swap does (a hop of a chain is then two memory latencies, not
+          // three).  Nobody can be rebuilding that list: its person is assigned until this very bid evicts it.
+          const int spec = ok ? ((t.v1 == t.v2 && o1 >= 0 && o2 < 0) ? -1 : o1) : -1;
+          if (spec >= 0) load_list(s, spec, lane, N);
+          if (!ok) {
             res = -3;
           } else if (lane == 0) {
             int j = t.j1, own_read = o1;
@@ -1454,11 +1471,13 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
               res = -2;
               __nanosleep(400);
             } else if (parked) {
-              res = -1;  // a standing tie: redo the step reproducibly
-              atomicExch(&ctrl->a_tie, 1);
-              atomicExch(&ctrl->a_stop, 1);
-              atomicAdd(&ctrl->a_parked, 1);
-              atomicSub(&ctrl->a_active, 1);
+              // a standing tie.  One or two of them occur in tie-free instances too (two values that are equal to the
+              // last bit while nothing around them moves any more): the person is left to the tail, which ends in the
+              // augmenting-path kernel if the tie is still there.  Many of them mean duplicated cells: redo the step
+              // reproducibly.
+              res = -1;
+              if (atomicAdd(&ctrl->a_parked, 1) + 1 > 4) atomicExch(&ctrl->a_tie, 1), atomicExch(&ctrl->a_stop, 1);
+              if (atomicSub(&ctrl->a_active, 1) - 1 <= stop_nu) atomicExch(&ctrl->a_stop, 1);
             } else {
               res = -2;
             }
@@ -1470,7 +1489,10 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
             if (res != -1 && ld_relaxed_s32(&ctrl->a_stop) != 0) res = -1;
           }
           res = __shfl_sync(0xffffffffu, res, 0);
-          if (res >= 0) i = res, tie_tries = 0;
+          if (res >= 0) {
+            if (res == spec) L = N, have = true;
+            i = res, tie_tries = 0;
+          }
           if (res == -1 || res == -3) break;
         }
         if (lane == 0) s_res = res, s_person = i;
@@ -3354,7 +3376,7 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   int aug_nu = opt.lap_aug_nu;
   if (n == m && opt.lap_aug_nu_square >= 0) aug_nu = opt.lap_aug_nu_square;
   // asynchronous wide kernel: the exact phase of a rectangular step with candidate lists and the master/helper tail
-  bool use_async = opt.lap_async != 0 && n < m && use_lists != 0 && mh_tail && tail_nu > 0 && s.pcls == nullptr &&
+  bool use_async = opt.lap_async != 0 && opt.deterministic == 0 && n < m && use_lists != 0 && mh_tail && tail_nu > 0 && s.pcls == nullptr &&
                    m >= 256 && nphases == 1 && s.list_k == LIST_K;
   int async_blocks = 0;
   const int async_threads = opt.lap_async_threads == 128 ? 128 : 256;

@@ -22,6 +22,7 @@ struct mcd_options {
   int certify = 1;            // "certify": dual certificate sweep after every assignment solve
   int debug = 0;              // "debug": per-step solver counters on stderr
   int corr_only = 0;          // "corr_only": mcd_cell2cell stops after K2 (matrix resident for the view calls)
+  int deterministic = 0;      // "deterministic": round-synchronous solver kernels only (fixed bid order; see lap.async)
   int ozaki_slices = 0;       // "ozaki.slices": 0 = automatic (mcd_ozaki_slices_for)
   int ozaki_align = 1;        // "ozaki.align": wave alignment of the K2c producers
   int ozaki_plan = 1;         // "ozaki.plan": unit order of a K2c pass
@@ -44,7 +45,7 @@ struct mcd_options {
   int lap_prefetch_rows = 1;  // "lap.prefetch_rows": symmetric tail prefetches the likely next bidder's row into L2
   int lap_async = 1;          // "lap.async": asynchronous (round-free) wide kernel for the rectangular steps
   int lap_async_nu = 0;       // "lap.async_nu": rounds with more bidders than this stay round-synchronous (0 = none)
-  int lap_async_threads = 256;  // "lap.async_threads": threads per worker CTA (128 or 256)
+  int lap_async_threads = 128;  // "lap.async_threads": threads per worker CTA (128 or 256)
   int lap_async_blocks_per_sm = 0;  // "lap.async_blocks_per_sm": 0 = as many as fit
   int lap_async_stop = 8;     // "lap.async_stop": unassigned persons at which the master/helper tail takes over
   int lap_tail_nu = -1;       // "lap.tail_nu": -1 = kernel default
