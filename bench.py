@@ -54,7 +54,7 @@ def load_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
     capture of `scripts/profile_pass.py C5` (newest profiles/r01_C5_*_ncu_summary.json).  Valid for the C5 workload."""
     p = next((q for q in (os.path.join(ROOT, "profiles", n) for n in (
-        "r02_C5_ncu_summary.json", "r01_C5_v6_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json",
+        "r02_C5_async_ncu_summary.json", "r02_C5_ncu_summary.json", "r01_C5_v6_ncu_summary.json", "r01_C5_ozaki_ncu_summary.json",
         "r01_C5_final_ncu_summary.json")) if os.path.exists(q)), "")
     out = {}
     if not os.path.exists(p):
@@ -715,16 +715,18 @@ def main():
                 rooflines["standardize"]["traffic"] = max(tr[k1])
             if corr_kernel in tr:
                 rooflines["corr"]["traffic"] = tr[corr_kernel][0]
-            if "lap_auction_kernel" in tr:
-                rooflines["lap"]["traffic"] = tr["lap_auction_kernel"][0]
-                rooflines["lap"]["traffic_note"] = ("one wide-round launch of lap_auction_kernel (a 10k x 40k step) in the "
-                                                    "committed capture profiles/r02_C5_ncu_summary.json; per-kernel "
-                                                    "DRAM bytes of every solver kernel are listed there")
+            lapk = next((k for k in ("lap_async_kernel", "lap_auction_kernel") if k in tr), None)
+            if lapk is not None:
+                rooflines["lap"]["traffic"] = tr[lapk][0]
+                rooflines["lap"]["traffic_note"] = ("one launch of %s (the wide phase of a 10k x 40k step: 3.2 GB cost block) in "
+                                                    "the committed capture profiles/r02_C5_async_ncu_summary.json; per-kernel "
+                                                    "DRAM bytes of the other solver kernels are listed there and in "
+                                                    "r02_C5_sym_ncu_summary.json" % lapk)
         dominant = max((("standardize", t_std), ("corr", t_corr), ("lap", t_lap)), key=lambda kv: kv[1])[0]
         roof = dict(rooflines[dominant])
         roof["kernel"] = {"standardize": "standardize_digits / standardize_rows", "corr": corr_kernel,
-                          "lap": "lap_auction_kernel + lap_tail_mh_kernel / lap_tail_cluster_kernel (assignment "
-                                 "solver, all steps)"}[dominant]
+                          "lap": "lap_async_kernel + lap_tail_mh_kernel (rectangular steps), lap_auction_kernel + "
+                                 "lap_tail_sym_kernel (square step): assignment solver, all steps"}[dominant]
         roof["algorithmic_bytes"] = {"standardize": std_bytes, "corr": None, "lap": lap_bytes_alg}[dominant]
         line = {
             "metric": METRIC, "value": ms_dev * 1e-3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "macrodna_b200", "libmacrodna_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 pats = ["UTCIMMA", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "STTM", "DMMA", "HMMA", "IMMA", "SYNCS",
-        "UCGABAR", "REDUX", "ATOMG", "RED\\."]
+        "UCGABAR", "REDUX", "ATOMG", "RED\\.", "UBLKPF"]
 cur = None
 counts = collections.OrderedDict()
 for line in sass.splitlines():
@@ -24,7 +24,7 @@ for line in sass.splitlines():
     for p in pats:
         if re.search(r"\b" + p, line):
             counts[cur][p.replace("\\.", "")] += 1
-            if p.startswith("UTC") or p in ("UTMALDG", "UBLKCP"):
+            if p.startswith("UTC") or p in ("UTMALDG", "UBLKCP", "UBLKPF") or (p == "ATOMG" and "CAS.128" in line):
                 mm = re.search(r"\b(" + p + r"[.\w]*)", line)
                 if mm:
                     counts[cur]["  " + mm.group(1)] += 1
