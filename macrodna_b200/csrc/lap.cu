@@ -1567,7 +1567,9 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
     }
     if (tid == 0) {
       const int nu = s_base;
-      const bool tie = !cont && ctrl->a_tie != 0 && nu > 0;  // (no fallback behind a hand-over from the synchronous kernel)
+      // exact ties, or the bid budget is spent (no instance measured comes near it): the synchronous kernel redoes the
+      // step (no such fallback behind a hand-over from the synchronous kernel)
+      const bool tie = !cont && (ctrl->a_tie != 0 || ctrl->a_guard != 0) && nu > 0;
       ctrl->a_fallback = tie ? 1 : 0;
       const bool aborted = (ctrl->a_guard != 0 || nu > max_nu) && !tie;
       ctrl->cnt[0] = nu;
@@ -2680,66 +2682,92 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_mh_kernel(LapState s
       sweeps += nfail;
       if (nfail > 0) __syncthreads();  // (uniform) the bids recorded by the failure loop above
       const long long c2 = clock64();
-      // ---- 3. resolution by threads 0..MH_NU-1, one bidder each
-      int person_out = -1;
-      bool applied = false;
-      if (tid < MH_NU) {
-        const bool live = tid < nu;
-        const int j = live ? s_bj[tid] : -1;
-        const unsigned long long key = live ? s_key[tid] : 0ull;
-        bool win = live;
-        if (nu <= 32) {
-          // (warp 0 only) the lanes bidding on the same object find each other with one match instruction
-          for (unsigned g = __match_any_sync(0xffffffffu, live ? j : -1 - lane) & ~(1u << lane); g != 0u; g &= g - 1u)
-            if (s_key[__ffs(g) - 1] > key) win = false;  // (keys carry the person: never equal)
-        } else if (live) {
-          for (int q = 0; q < nu; ++q)  // broadcast reads
-            if (s_bj[q] == j && s_key[q] > key) win = false;
+      // ---- 3. resolution, one bidder per thread
+      auto resolve = [&](bool live, bool win, int& person_out, bool& applied) {
+        person_out = -1;
+        applied = false;
+        if (!live) return;
+        const int j = s_bj[tid];
+        const int i = s_list[cur][tid];
+        person_out = i;  // re-queue unless the bid is applied
+        if (!win) return;
+        const double p_old = s.price[j];
+        const double p_new = p_old + s_gam[tid];
+        const int prev = s.owner[j];
+        const double defend = class_defends<false>(s, i, prev, s_gam[tid]);
+        if (defend > 0.0) {  // the owner's class has settled lower: the owner raises the price and keeps the object
+          s.price[j] = p_old + defend;
+          s.profit[prev] -= defend;
+          applied = true;  // (progress; the bidder is re-queued: person_out stays i)
+        } else if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
+          applied = true;
+          person_out = prev;  // the evicted owner (or -1) bids next round
+          s.owner[j] = i;
+          if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
+          s.price[j] = p_new;
+          s.col4row[i] = j;
+          const double prof = (s_bval[tid] + p_old) - p_new;
+          s.profit[i] = prof;
+          class_settle(s, i, prof);
+          if (prev >= 0) s.col4row[prev] = -1;
         }
-        if (live) {
-          const int i = s_list[cur][tid];
-          person_out = i;  // re-queue unless the bid is applied
-          if (win) {
-            const double p_old = s.price[j];
-            const double p_new = p_old + s_gam[tid];
-            const int prev = s.owner[j];
-            const double defend = class_defends<false>(s, i, prev, s_gam[tid]);
-            if (defend > 0.0) {  // the owner's class has settled lower: the owner raises the price and keeps the object
-              s.price[j] = p_old + defend;
-              s.profit[prev] -= defend;
-              applied = true;  // (progress; the bidder is re-queued: person_out stays i)
-            } else if (prev < 0 || s_gam[tid] > GAMMA_TIE) {
-              applied = true;
-              person_out = prev;  // the evicted owner (or -1) bids next round
-              s.owner[j] = i;
-              if (s.pcls != nullptr) s.ocls[j] = s.pcls[i];
-              s.price[j] = p_new;
-              s.col4row[i] = j;
-              const double prof = (s_bval[tid] + p_old) - p_new;
-              s.profit[i] = prof;
-              class_settle(s, i, prof);
-              if (prev >= 0) s.col4row[prev] = -1;
-            }
+      };
+      if (nu <= 32) {
+        // the usual case: warp 0 resolves, compacts the next bidder list and publishes the counts by itself (one
+        // CTA barrier per resolution instead of two)
+        if (warp == 0) {
+          const bool live = lane < nu;
+          const int j = live ? s_bj[lane] : -1 - lane;
+          const unsigned long long key = live ? s_key[lane] : 0ull;
+          bool win = live;
+          if (nu <= 4) {
+            for (int q = 0; q < nu; ++q)
+              if (s_bj[q] == j && s_key[q] > key) win = false;  // (keys carry the person: never equal)
+          } else {
+            // the lanes bidding on the same object find each other with one match instruction
+            for (unsigned g = __match_any_sync(0xffffffffu, j) & ~(1u << lane); g != 0u; g &= g - 1u)
+              if (s_key[__ffs(g) - 1] > key) win = false;
+          }
+          int person_out;
+          bool applied;
+          resolve(live, win, person_out, applied);
+          const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+          const unsigned acc = __ballot_sync(0xffffffffu, applied);
+          if (person_out >= 0) s_list[cur ^ 1][__popc(has & ((1u << lane) - 1u))] = person_out;
+          if (lane == 0) s_cnt[1] = __popc(has), s_cnt[2] = __popc(acc), s_cnt[0] = 0;
+        }
+        __syncthreads();
+      } else {
+        int person_out = -1;
+        bool applied = false;
+        if (tid < MH_NU) {
+          const bool live = tid < nu;
+          const int j = live ? s_bj[tid] : -1;
+          const unsigned long long key = live ? s_key[tid] : 0ull;
+          bool win = live;
+          if (live)
+            for (int q = 0; q < nu; ++q)  // broadcast reads
+              if (s_bj[q] == j && s_key[q] > key) win = false;
+          resolve(live, win, person_out, applied);
+          // ordered compaction of the next bidder list over the resolving warps
+          const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+          const unsigned acc = __ballot_sync(0xffffffffu, applied);
+          if (lane == 0) s_wcnt[warp] = __popc(has), s_wacc[warp] = __popc(acc);
+        }
+        __syncthreads();
+        if (tid < MH_NU) {
+          int off = 0;
+          for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+          const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
+          if (person_out >= 0) s_list[cur ^ 1][off + __popc(has & ((1u << lane) - 1u))] = person_out;
+          if (tid == 0) {
+            int tn = 0, ta = 0;
+            for (int w = 0; w < MH_NU / 32; ++w) tn += s_wcnt[w], ta += s_wacc[w];
+            s_cnt[1] = tn, s_cnt[2] = ta, s_cnt[0] = 0;
           }
         }
-        // ordered compaction of the next bidder list over the resolving warps
-        const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
-        const unsigned acc = __ballot_sync(0xffffffffu, applied);
-        if (lane == 0) s_wcnt[warp] = __popc(has), s_wacc[warp] = __popc(acc);
+        __syncthreads();
       }
-      __syncthreads();
-      if (tid < MH_NU) {
-        int off = 0;
-        for (int w = 0; w < warp; ++w) off += s_wcnt[w];
-        const unsigned has = __ballot_sync(0xffffffffu, person_out >= 0);
-        if (person_out >= 0) s_list[cur ^ 1][off + __popc(has & ((1u << lane) - 1u))] = person_out;
-        if (tid == 0) {
-          int tn = 0, ta = 0;
-          for (int w = 0; w < MH_NU / 32; ++w) tn += s_wcnt[w], ta += s_wacc[w];
-          s_cnt[1] = tn, s_cnt[2] = ta, s_cnt[0] = 0;
-        }
-      }
-      __syncthreads();
       const int nu_next = s_cnt[1], accepted = s_cnt[2];
       rounds++;
       bids += nu;
@@ -3379,8 +3407,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
   bool use_async = opt.lap_async != 0 && opt.deterministic == 0 && n < m && use_lists != 0 && mh_tail && tail_nu > 0 && s.pcls == nullptr &&
                    m >= 256 && nphases == 1 && s.list_k == LIST_K;
   int async_blocks = 0;
-  const int async_threads = opt.lap_async_threads == 128 ? 128 : 256;
-  const void* async_fn = async_threads == 128 ? (const void*)lap_async_kernel<128> : (const void*)lap_async_kernel<256>;
+  const int async_threads = opt.lap_async_threads == 64 ? 64 : (opt.lap_async_threads == 256 ? 256 : 128);
+  const void* async_fn = async_threads == 64    ? (const void*)lap_async_kernel<64>
+                         : async_threads == 128 ? (const void*)lap_async_kernel<128>
+                                                : (const void*)lap_async_kernel<256>;
   if (use_async) {
     int aper = 0;
     MCD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aper, async_fn, async_threads, 0));
