@@ -1322,10 +1322,11 @@ __device__ __forceinline__ bool list_bid_pw(const LapState& s, const ListRegs& L
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, int max_nu, int cont) {
+__global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, int max_nu, int cont, int fallback_ok) {
   LapCtrl* ctrl = s.ctrl;
   if (ctrl->finished || s.flags[0]) return;  // uniform
-  GridBarrier grid{&ctrl->barrier[MAX_PHASES - 1], 0u};  // (slot 0 belongs to the synchronous kernel's launch)
+  GridBarrier grid{&ctrl->barrier[MAX_PHASES - 1 - cont], 0u};  // (slot 0: the synchronous kernel's launch; a launch
+                                                                    // that continues another one has a counter of its own)
   __shared__ double cand_v[NT * CAND_T];
   __shared__ int cand_j[NT * CAND_T];
   __shared__ double red[(NT / 32)];
@@ -1569,7 +1570,7 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
       const int nu = s_base;
       // exact ties, or the bid budget is spent (no instance measured comes near it): the synchronous kernel redoes the
       // step (no such fallback behind a hand-over from the synchronous kernel)
-      const bool tie = !cont && (ctrl->a_tie != 0 || ctrl->a_guard != 0) && nu > 0;
+      const bool tie = fallback_ok && (ctrl->a_tie != 0 || ctrl->a_guard != 0) && nu > 0;
       ctrl->a_fallback = tie ? 1 : 0;
       const bool aborted = (ctrl->a_guard != 0 || nu > max_nu) && !tie;
       ctrl->cnt[0] = nu;
@@ -3442,9 +3443,10 @@ int mcd_launch_lap(mcd_context* h, const double* W, int64_t n, int64_t m, int64_
         h->launches++;
         cont = 1;
       }
-      void* aargs[] = {&s, &stop_nu, &max_nu, &cont};
+      int fallback_ok = cont == 0 ? 1 : 0;
+      void* aargs[] = {&s, &stop_nu, &max_nu, &cont, &fallback_ok};
       MCD_CUDA(h, cudaLaunchCooperativeKernel(async_fn, dim3(async_blocks), dim3(async_threads), aargs, 0, h->stream));
-      if (cont == 0) {  // exact ties: the step is redone round-synchronously (a no-op launch otherwise)
+      if (fallback_ok) {  // exact ties: the step is redone round-synchronously (a no-op launch otherwise)
         int yes = 1;
         void* args[] = {&s, &factor, &ph, &tail_nu, &use_lists, &list_min_nu, &aug_nu, &rank_select, &yes};
         MCD_CUDA(h, cudaLaunchCooperativeKernel((const void*)lap_auction_kernel, dim3(blocks), dim3(LAP_THREADS), args,
