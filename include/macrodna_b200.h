@@ -65,8 +65,11 @@ typedef struct {
   int64_t lap_bytes;      /* cost bytes scanned by bidding + augmentation, all steps      */
   int64_t lap_aug_rows;   /* persons finished by shortest-augmenting-path instead of bids */
   int64_t lap_aug_steps;  /* Dijkstra steps of those augmentations                        */
-  int64_t lap_cycles[8];  /* SM cycles of CTA 0. wide kernel: bidding, barrier 1, resolution, barrier 2;
-                             cluster kernel: scan, wait for partials, resolve + send, wait for packet */
+  int64_t lap_cycles[8];  /* [0..3] synchronous wide kernel, SM cycles of CTA 0: bidding, barrier 1, resolution,
+                             barrier 2; steps run by the asynchronous wide kernel add ns instead: bidding until CTA 0
+                             ran out of work, drain of the other workers, epilogue, and the persons parked on ties.
+                             [4..7] narrow-round kernels, SM cycles of the resolving CTA: scan / bidding, wait for
+                             partials / list rebuilds, resolution, (first cluster kernel only) wait for the packet */
   double step_ms[MCD_MAX_STEP_STATS];
   int64_t step_rounds[MCD_MAX_STEP_STATS];
   int64_t step_bids[MCD_MAX_STEP_STATS];
