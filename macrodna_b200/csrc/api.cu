@@ -1504,7 +1504,9 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
     }
   }
   const int64_t launches0 = h->launches;
-  MCD_CUDA(h, cudaEventRecord(get_event(h, 6), h->stream));
+  // (events 6 / 7 and 8 .. 8 + steps belong to mcd_subinstance_steps, which the class-free re-solve of a replicate runs
+  //  on this handle: the sweep times itself with events of its own)
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 96), h->stream));
   std::vector<mcd_lap_counters> hc((size_t)(nsteps * batch));
   std::vector<mcd_lap_cert> hcert((size_t)(nsteps * batch));
   if (stats) memset(stats, 0, sizeof *stats);
@@ -1620,11 +1622,11 @@ int mcd_subinstance_sweep(mcd_handle h, int64_t nrep, const int32_t* rna_rows, i
       if (cert_gap) cert_gap[r0 + b] = h->opt.certify ? g : -1.0;
     }
   }
-  MCD_CUDA(h, cudaEventRecord(get_event(h, 7), h->stream));
+  MCD_CUDA(h, cudaEventRecord(get_event(h, 97), h->stream));
   MCD_CUDA(h, cudaStreamSynchronize(h->stream));
   if (stats) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, get_event(h, 6), get_event(h, 7));
+    cudaEventElapsedTime(&ms, get_event(h, 96), get_event(h, 97));
     stats->ms_lap = ms;
     stats->ms_total = ms;
     stats->ms_h2d = host_enqueue_ms;
