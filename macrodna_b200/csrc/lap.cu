@@ -2360,7 +2360,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) lap_tail_sym_kernel(LapState 
       tq[2] += clock64() - c2;
     }
     tq[0] += c1 - c0;
-    if (nu == 1) tq[3] += c1 - c0;  // (research counter: scan cycles of single-bidder rounds)
+    if (nu == 1) tq[3] += c1 - c0;  // (t_phase[7] of this kernel: scan cycles of the single-bidder rounds)
     __syncthreads();
     rounds++;
     bids += nu;
