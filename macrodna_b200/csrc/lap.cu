@@ -1419,6 +1419,11 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
           // three).  Nobody can be rebuilding that list: its person is assigned until this very bid evicts it.
           const int spec = ok ? ((t.v1 == t.v2 && o1 >= 0 && o2 < 0) ? -1 : o1) : -1;
           if (spec >= 0) load_list(s, spec, lane, N);
+          // ... and only a compare-and-swap that succeeds at the first attempt proves it: the word of the object was
+          // unchanged from the gather to the swap, so that person held it all the time (taking an owned object back
+          // raises its price).  After a retry the person may have been evicted, had its list rebuilt under these very
+          // loads, and come back: the speculative copy is then dropped.
+          int spec_ok = 0;
           if (!ok) {
             res = -3;
           } else if (lane == 0) {
@@ -1446,6 +1451,7 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
               if (cas128(s.pw + j, e0, e1, (unsigned long long)__double_as_longlong(p_new), (unsigned long long)(unsigned)i)) {
                 prev = own_cur;
                 placed = true;
+                spec_ok = first ? 1 : 0;
                 // the sweeps' copy of the price: prices are >= 0, so their bit patterns order like the values and an
                 // atomic max keeps the copy monotone even when two winners' updates arrive out of order
                 atomicMax(reinterpret_cast<unsigned long long*>(s.price + j), (unsigned long long)__double_as_longlong(p_new));
@@ -1490,8 +1496,9 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
             if (res != -1 && ld_relaxed_s32(&ctrl->a_stop) != 0) res = -1;
           }
           res = __shfl_sync(0xffffffffu, res, 0);
+          spec_ok = __shfl_sync(0xffffffffu, spec_ok, 0);
           if (res >= 0) {
-            if (res == spec) L = N, have = true;
+            if (res == spec && spec_ok) L = N, have = true;
             i = res, tie_tries = 0;
           }
           if (res == -1 || res == -3) break;
