@@ -602,6 +602,8 @@ int fold_step_records(mcd_context* h, int64_t M, int64_t N, int64_t nsteps, cons
       for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].t_phase[q]);
       fprintf(stderr, " async_us=");
       for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].a_ts[q] / 1000);
+      fprintf(stderr, " async_kbids=");
+      for (int q = 0; q < 8; ++q) fprintf(stderr, "%lld ", hc[s].a_hops[q] / 1000);
       fprintf(stderr, "\n");
     }
   }

@@ -115,6 +115,7 @@ struct LapCtrl {
   int a_active, a_stop, a_parked, a_guard;
   unsigned long long a_bids;
   unsigned long long a_t0;
+  unsigned long long a_hops;
   int a_tie;       // an exact tie was met (two equal best values, or a bid that cannot raise a price)
   int a_fallback;  // ... so the step is redone by the round-synchronous kernel
 };
@@ -1369,6 +1370,7 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
     ctrl->a_guard = 0;
     ctrl->a_tie = 0;
     ctrl->a_fallback = 0;
+    ctrl->a_hops = 0ull;
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     ctrl->a_t0 = now;
@@ -1460,6 +1462,7 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
               first = false;
             }
             bids++;
+            atomicAdd(&ctrl->a_hops, 1ull);  // (fire and forget; read by the debug time line only)
             if (placed) {
               res = prev;  // -1: the chain ended on a free object
               if (prev < 0) {
@@ -1470,6 +1473,7 @@ __global__ void __launch_bounds__(NT) lap_async_kernel(LapState s, int stop_nu, 
                   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                   const int slot = left == stop_nu ? 7 : 12 - (31 - __clz(left));  // 4096 -> 0 ... 64 -> 6
                   s.counters->a_ts[slot] = (long long)(now - ctrl->a_t0);
+                  s.counters->a_hops[slot] = (long long)ctrl->a_hops;
                 }
               }
             } else if (parked && ++tie_tries <= 32) {
@@ -3019,7 +3023,7 @@ __global__ void lap_ctrl_init_kernel(LapCtrl* ctrl, mcd_lap_counters* counters, 
   if (zero_counters) {
     counters->rounds = counters->bids = counters->bytes = counters->aug_rows = counters->aug_steps = 0;
     counters->status = 0;
-    for (int q = 0; q < 8; ++q) counters->t_phase[q] = 0, counters->a_ts[q] = 0;
+    for (int q = 0; q < 8; ++q) counters->t_phase[q] = 0, counters->a_ts[q] = 0, counters->a_hops[q] = 0;
   }
 }
 

@@ -176,6 +176,7 @@ struct mcd_lap_counters {  // device-resident, one per solve
                          // cluster kernel: scan, wait partials, resolve+send, wait packet
   long long a_ts[8];     // asynchronous wide kernel (debug): ns from its start until <= 4096, 2048, 1024, 512, 256, 128, 64,
                          // stop_nu persons were left unassigned
+  long long a_hops[8];   // ... and the bids made until then
 };
 struct mcd_lap_cert {  // device-resident, one per solve: the dual certificate (lap.cu, lap_cert_* kernels)
   double lambda;         // min price over the assigned objects
