@@ -34,6 +34,16 @@ def test_exports_every_declared_symbol():
     assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
 
 
+def test_every_handle_option_is_documented_in_the_header():
+    """mcd_set_option's table (csrc/api.cu) and the option list in the header's comment must not drift apart."""
+    src = open(os.path.join(ROOT, "macrodna_b200", "csrc", "api.cu")).read()
+    names = re.findall(r'MCD_OPT_[ID]\("([a-z0-9_.]+)"', src)
+    assert len(names) >= 30 and len(set(names)) == len(names)
+    hdr = open(os.path.join(ROOT, "include", "macrodna_b200.h")).read()
+    missing = [n for n in names if '"%s"' % n not in hdr]
+    assert not missing, missing
+
+
 def test_pure_host_entry_points():
     lib = _lib.load_library()
     assert lib.mcd_abi_version() == 2
