@@ -55,6 +55,19 @@ def test_async_equals_synchronous_and_scipy(handle, synchronous, shape):
         assert (col_b == col_a).all() and obj_b == obj_a
 
 
+@pytest.mark.parametrize("shape", [(1, 256), (3, 1000), (8, 5000), (9, 5000), (255, 256), (2, 40000)])
+def test_async_few_persons(handle, shape):
+    """At most 8 persons: the asynchronous kernel stops before its first bid and the tail starts from scratch; 9: one
+    bid is enough to hand over."""
+    from scipy.optimize import linear_sum_assignment
+
+    n, m = shape
+    w = np.random.default_rng(n + m).standard_normal((n, m)) * 0.1
+    col, _ = _lap(handle, w)
+    r, c = linear_sum_assignment(w, maximize=True)
+    assert (col == c).all()
+
+
 def test_async_starved_group(handle, synchronous):
     """More persons than objects in one group: the excess persons fight a price war over the group's objects before
     they leave it (long eviction chains, the regime the chain-following workers are for)."""
